@@ -1,0 +1,439 @@
+// C ABI of libavn_gp.so: argument checking, workspace layout and the launch sequences.
+// See include/avn_gp.h for the contract and the reference call sites each entry point replaces.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "kernels.cuh"
+
+using namespace avn;
+
+static thread_local std::string g_err;
+static int fail(const char* msg) {
+  g_err = msg;
+  return -1;
+}
+static int fail_cuda(const char* where, cudaError_t e) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return -2;
+}
+
+struct avn_gp {
+  avn_model_desc desc;
+  KernDesc kd;
+  WarpProgs progs;
+  const double* X = nullptr;
+  const double* y = nullptr;
+  int64_t N = 0;
+  int64_t launches = 0;
+  bool has_xwarp = false;
+};
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline int64_t npad_of(int64_t N) { return align_up(N < 1 ? 1 : N, TILE); }
+
+extern "C" const char* avn_last_error(void) { return g_err.c_str(); }
+extern "C" int avn_version(void) { return 100; }
+
+extern "C" int avn_gp_create(const avn_model_desc* desc, avn_gp** out) {
+  if (!desc || !out) return fail("avn_gp_create: null argument");
+  if (desc->d < 1 || desc->d > AVN_MAX_D) return fail("avn_gp_create: d out of range [1,16]");
+  if (desc->nkern < 1 || desc->nkern > AVN_MAX_KERN) return fail("avn_gp_create: nkern out of range [1,4]");
+  int nrq = 0;
+  for (int k = 0; k < desc->nkern; k++) {
+    if (desc->kern[k] < AVN_RBF || desc->kern[k] > AVN_RATQUAD) return fail("avn_gp_create: unknown kernel id");
+    if (desc->kern[k] == AVN_RATQUAD) nrq++;
+    if (k > 0 && desc->op[k - 1] != AVN_ADD && desc->op[k - 1] != AVN_MUL) return fail("avn_gp_create: bad kernel op");
+  }
+  if (nrq > 1) return fail("avn_gp_create: at most one RatQuad kernel (gpmcmc.py:287)");
+  avn_gp* gp = new avn_gp();
+  gp->desc = *desc;
+  KernDesc& kd = gp->kd;
+  memset(&kd, 0, sizeof(kd));
+  kd.d = desc->d;
+  kd.nkern = desc->nkern;
+  kd.noise = desc->noise ? 1 : 0;
+  kd.has_alpha = nrq;
+  kd.jitter = desc->jitter;
+  for (int k = 0; k < desc->nkern; k++) {
+    kd.kern[k] = desc->kern[k];
+    kd.op[k] = desc->op[k];
+  }
+  int n_iw = 0;
+  for (int m = 0; m < desc->d; m++) {
+    const avn_warp_prog& p = desc->xwarp[m];
+    if (p.nstages < 0 || p.nstages > AVN_MAX_STAGES || p.nparams < 0 || p.nparams > AVN_MAX_WPARAMS) {
+      delete gp;
+      return fail("avn_gp_create: x warp program out of range");
+    }
+    gp->progs.xw[m] = p;
+    if (p.nstages > 0) {
+      gp->has_xwarp = true;
+      n_iw += p.nparams;
+    }
+  }
+  for (int m = desc->d; m < AVN_MAX_D; m++) memset(&gp->progs.xw[m], 0, sizeof(avn_warp_prog));
+  const avn_warp_prog& yp = desc->ywarp;
+  if (yp.nstages < 0 || yp.nstages > AVN_MAX_STAGES || yp.nparams < 0 || yp.nparams > AVN_MAX_WPARAMS) {
+    delete gp;
+    return fail("avn_gp_create: y warp program out of range");
+  }
+  gp->progs.yw = yp;
+  int p = 0;
+  kd.off_gv = p;
+  if (kd.noise) p += 1;
+  kd.off_l = p;
+  p += kd.d * kd.nkern;
+  kd.off_kv = p;
+  p += kd.nkern;
+  kd.off_iw = p;
+  kd.n_iw = n_iw;
+  p += n_iw;
+  kd.off_cw = p;
+  kd.n_cw = yp.nstages > 0 ? yp.nparams : 0;
+  p += kd.n_cw;
+  kd.off_alpha = p;
+  if (kd.has_alpha) p += 1;
+  kd.P = p;
+  *out = gp;
+  return 0;
+}
+
+extern "C" void avn_gp_destroy(avn_gp* gp) { delete gp; }
+extern "C" int avn_gp_num_params(const avn_gp* gp) { return gp ? gp->kd.P : -1; }
+extern "C" int64_t avn_gp_last_launch_count(const avn_gp* gp) { return gp ? gp->launches : -1; }
+
+extern "C" int avn_gp_set_data(avn_gp* gp, const double* X_dev, const double* y_dev, int64_t N) {
+  if (!gp || !X_dev || !y_dev) return fail("avn_gp_set_data: null argument");
+  if (N < 1 || N > 65536) return fail("avn_gp_set_data: N out of range [1,65536]");
+  gp->X = X_dev;
+  gp->y = y_dev;
+  gp->N = N;
+  return 0;
+}
+
+static void layout(const avn_gp* gp, int64_t B, avn_ws_layout* L) {
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = npad_of(gp->N), nb = npad / TILE, ntiles = nb * (nb + 1) / 2;
+  int64_t off = 0;
+  auto take = [&](int64_t doubles) {
+    int64_t o = off;
+    off += align_up(doubles * 8, 256);
+    return o;
+  };
+  L->npad = npad;
+  L->nb = nb;
+  L->xw = take(B * npad * kd.d);
+  L->dxw = take(gp->has_xwarp ? B * npad * kd.d * MAXWP : 0);
+  L->xs = take(B * kd.nkern * npad * kd.d);
+  L->x2 = take(B * kd.nkern * npad);
+  L->z = take(B * npad);
+  L->dz = take(kd.n_cw > 0 ? B * npad * MAXWP : 0);
+  L->wstat = take(B * WSTAT);
+  L->kl = take(B * npad * npad);
+  L->t = take(B * npad * npad);
+  L->beta = take(B * npad);
+  L->alpha = take(B * npad);
+  L->gpart = take(B * ntiles * MAXACC);
+  L->gxpart = take(gp->has_xwarp ? B * nb * npad * kd.d : 0);
+  L->total = off;
+}
+
+static WsPtrs ws_ptrs(const avn_ws_layout& L, void* ws) {
+  char* base = static_cast<char*>(ws);
+  auto at = [&](int64_t o) { return reinterpret_cast<double*>(base + o); };
+  WsPtrs p;
+  p.xw = at(L.xw); p.dxw = at(L.dxw); p.xs = at(L.xs); p.x2 = at(L.x2); p.z = at(L.z); p.dz = at(L.dz);
+  p.wstat = at(L.wstat); p.kl = at(L.kl); p.t = at(L.t); p.beta = at(L.beta); p.alpha = at(L.alpha);
+  p.gpart = at(L.gpart); p.gxpart = at(L.gxpart);
+  return p;
+}
+
+extern "C" size_t avn_gp_workspace_bytes(const avn_gp* gp, int64_t B) {
+  if (!gp || gp->N < 1 || B < 1) return 0;
+  avn_ws_layout L;
+  layout(gp, B, &L);
+  return (size_t)L.total;
+}
+
+extern "C" int avn_gp_workspace_layout(const avn_gp* gp, int64_t B, avn_ws_layout* out) {
+  if (!gp || !out || gp->N < 1 || B < 1) return fail("avn_gp_workspace_layout: bad argument");
+  layout(gp, B, out);
+  return 0;
+}
+
+template <typename K>
+static cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define LAUNCH_CHECK(name)                                  \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return fail_cuda(name, e__);    \
+    gp->launches++;                                         \
+  } while (0)
+
+// conversions + scaled inputs for B samples
+static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st) {
+  warp_kernel<<<(unsigned)B, 256, 0, st>>>(gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W);
+  LAUNCH_CHECK("warp_kernel");
+  return 0;
+}
+
+static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, double* Kout,
+                   cudaStream_t st) {
+  const KernDesc& kd = gp->kd;
+  const int64_t nb = npad / TILE, ntiles = nb * (nb + 1) / 2;
+  size_t smem = (size_t)(2 * kd.nkern * TILE * kd.d + 2 * kd.nkern * TILE) * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = opt_in_smem(cov_kernel, smem);
+    if (e != cudaSuccess) return fail_cuda("cov_kernel smem", e);
+  }
+  cov_kernel<<<dim3((unsigned)ntiles, (unsigned)B), 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout);
+  LAUNCH_CHECK("cov_kernel");
+  return 0;
+}
+
+static const size_t kDiagSmem = (size_t)2 * TILE * (TILE + 1) * 8;
+
+// Cholesky K -> L in place (kl), diagonal-block inverses into t, then the rest of T = L^-1
+static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* info, int64_t npad, bool want_inverse,
+                      cudaStream_t st) {
+  const int nb = (int)(npad / TILE);
+  constexpr int BM = 128;
+  using PG = PotrfCfg<BM>::G;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = opt_in_smem(potrf_update_kernel<BM>, PG::SMEM_BYTES);
+    if (e == cudaSuccess) e = opt_in_smem(potrf_panel_kernel<BM>, PG::SMEM_BYTES);
+    if (e == cudaSuccess) e = opt_in_smem(trtri_row_kernel, TrtriG::SMEM_BYTES);
+    if (e == cudaSuccess) e = opt_in_smem(potrf_diag_kernel, kDiagSmem);
+    if (e != cudaSuccess) return fail_cuda("factor smem opt-in", e);
+    attr_done = true;
+  }
+  for (int k = 0; k < nb; k++) {
+    if (k > 0) {
+      int rows = (nb - k) * TILE;
+      potrf_update_kernel<BM><<<dim3((rows + BM - 1) / BM, (unsigned)B), PG::NTHREADS, PG::SMEM_BYTES, st>>>(kl, (int)npad, k);
+      LAUNCH_CHECK("potrf_update_kernel");
+    }
+    potrf_diag_kernel<<<(unsigned)B, 256, kDiagSmem, st>>>(kl, t, (int)npad, k, info);
+    LAUNCH_CHECK("potrf_diag_kernel");
+    if (k + 1 < nb) {
+      int rows = (nb - k - 1) * TILE;
+      potrf_panel_kernel<BM><<<dim3((rows + BM - 1) / BM, (unsigned)B), PG::NTHREADS, PG::SMEM_BYTES, st>>>(kl, t, (int)npad, k);
+      LAUNCH_CHECK("potrf_panel_kernel");
+    }
+  }
+  if (want_inverse) {
+    for (int i = 1; i < nb; i++) {
+      trtri_row_kernel<<<dim3(i, (unsigned)B), TrtriG::NTHREADS, TrtriG::SMEM_BYTES, st>>>(kl, t, (int)npad, i);
+      LAUNCH_CHECK("trtri_row_kernel");
+    }
+  }
+  return 0;
+}
+
+static int run_trsv_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, bool want_alpha, cudaStream_t st) {
+  size_t smem = (size_t)(npad + TILE + 32) * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = opt_in_smem(trsv_kernel, smem);
+    if (e != cudaSuccess) return fail_cuda("trsv smem", e);
+  }
+  trsv_kernel<<<(unsigned)B, 256, smem, st>>>(W.kl, W.t, W.z, (int)npad, W.beta, W.wstat);
+  LAUNCH_CHECK("trsv_kernel");
+  if (want_alpha) {
+    alpha_kernel<<<dim3((unsigned)(npad / TILE), (unsigned)B), 256, 0, st>>>(W.t, W.beta, (int)npad, W.alpha);
+    LAUNCH_CHECK("alpha_kernel");
+  }
+  return 0;
+}
+
+extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
+                          void* stream) {
+  if (!gp || !theta_dev || !K_dev || !ws_dev) return fail("avn_gp_cov: null argument");
+  if (gp->N < 1) return fail("avn_gp_cov: set_data first");
+  if (B < 1 || B > 65535) return fail("avn_gp_cov: B out of range [1,65535]");
+  avn_ws_layout L;
+  layout(gp, B, &L);
+  if (ws_bytes < (size_t)L.total) return fail("avn_gp_cov: workspace too small");
+  gp->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WsPtrs W = ws_ptrs(L, ws_dev);
+  int rc = run_warp(gp, theta_dev, B, W, L.npad, st);
+  if (rc) return rc;
+  return run_cov(gp, theta_dev, B, W, L.npad, K_dev, st);
+}
+
+extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B, double* ll_dev, double* grad_dev,
+                                  int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!gp || !theta_dev || !ll_dev || !info_dev || !ws_dev) return fail("avn_gp_loglik_grad: null argument");
+  if (gp->N < 1) return fail("avn_gp_loglik_grad: set_data first");
+  if (B < 1 || B > 65535) return fail("avn_gp_loglik_grad: B out of range [1,65535]");
+  avn_ws_layout L;
+  layout(gp, B, &L);
+  if (ws_bytes < (size_t)L.total) return fail("avn_gp_loglik_grad: workspace too small");
+  gp->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WsPtrs W = ws_ptrs(L, ws_dev);
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = L.npad, nb = L.nb, ntiles = nb * (nb + 1) / 2;
+  const bool want_grad = grad_dev != nullptr;
+  cudaError_t e = cudaMemsetAsync(info_dev, 0, sizeof(int32_t) * B, st);
+  if (e != cudaSuccess) return fail_cuda("memset info", e);
+  int rc = run_warp(gp, theta_dev, B, W, npad, st);
+  if (rc) return rc;
+  rc = run_cov(gp, theta_dev, B, W, npad, W.kl, st);
+  if (rc) return rc;
+  rc = run_factor(gp, B, W.kl, W.t, info_dev, npad, want_grad, st);
+  if (rc) return rc;
+  rc = run_trsv_alpha(gp, B, W, npad, want_grad, st);
+  if (rc) return rc;
+  if (want_grad) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      e = opt_in_smem(kinv_grad_kernel<false>, KinvG::SMEM_BYTES);
+      if (e == cudaSuccess) e = opt_in_smem(kinv_grad_kernel<true>, KinvG::SMEM_BYTES);
+      if (e != cudaSuccess) return fail_cuda("kinv_grad smem opt-in", e);
+      attr_done = true;
+    }
+    if (gp->has_xwarp)
+      kinv_grad_kernel<true><<<dim3((unsigned)ntiles, (unsigned)B), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
+          kd, (int)gp->N, (int)npad, theta_dev, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
+    else
+      kinv_grad_kernel<false><<<dim3((unsigned)ntiles, (unsigned)B), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
+          kd, (int)gp->N, (int)npad, theta_dev, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
+    LAUNCH_CHECK("kinv_grad_kernel");
+  }
+  finalize_kernel<<<(unsigned)B, 256, 0, st>>>(kd, gp->progs, (int)gp->N, (int)npad, (int)ntiles, want_grad ? 1 : 0,
+                                               theta_dev, W, info_dev, ll_dev, grad_dev);
+  LAUNCH_CHECK("finalize_kernel");
+  return 0;
+}
+
+// ---- predict -------------------------------------------------------------------------------------
+struct StateLayout {
+  int64_t hyp, alpha, xs, x2, t, total;  // byte offsets
+};
+static StateLayout state_layout(const avn_gp* gp) {
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = npad_of(gp->N);
+  StateLayout S;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    int64_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  S.hyp = take(sizeof(HypS));
+  S.alpha = take(npad * 8);
+  S.xs = take((int64_t)kd.nkern * npad * kd.d * 8);
+  S.x2 = take((int64_t)kd.nkern * npad * 8);
+  S.t = take(npad * npad * 8);
+  S.total = off;
+  return S;
+}
+
+extern "C" size_t avn_gp_state_bytes(const avn_gp* gp) {
+  if (!gp || gp->N < 1) return 0;
+  return (size_t)state_layout(gp).total;
+}
+
+__global__ void hyp_store_kernel(KernDesc kd, const double* __restrict__ theta, HypS* __restrict__ out) {
+  __shared__ HypS h;
+  for (int e = threadIdx.x; e < (int)(sizeof(HypS) / 8); e += blockDim.x) reinterpret_cast<double*>(&h)[e] = 0.0;
+  __syncthreads();
+  load_hyp(h, kd, theta);
+  __syncthreads();
+  for (int e = threadIdx.x; e < (int)(sizeof(HypS) / 8); e += blockDim.x)
+    reinterpret_cast<double*>(out)[e] = reinterpret_cast<double*>(&h)[e];
+}
+
+extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state_dev, size_t state_bytes,
+                                int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!gp || !theta_dev || !state_dev || !info_dev || !ws_dev) return fail("avn_gp_factorize: null argument");
+  if (gp->N < 1) return fail("avn_gp_factorize: set_data first");
+  if (gp->has_xwarp || gp->kd.n_cw > 0)
+    return fail("avn_gp_factorize: predict works on converted data; bake the warps on the host first (gpmcmc.py:364-399)");
+  avn_ws_layout L;
+  layout(gp, 1, &L);
+  StateLayout S = state_layout(gp);
+  if (ws_bytes < (size_t)L.total) return fail("avn_gp_factorize: workspace too small");
+  if (state_bytes < (size_t)S.total) return fail("avn_gp_factorize: state buffer too small");
+  gp->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WsPtrs W = ws_ptrs(L, ws_dev);
+  char* sb = static_cast<char*>(state_dev);
+  // T, alpha, xs, x2 are produced directly inside the state buffer
+  W.t = reinterpret_cast<double*>(sb + S.t);
+  W.alpha = reinterpret_cast<double*>(sb + S.alpha);
+  W.xs = reinterpret_cast<double*>(sb + S.xs);
+  W.x2 = reinterpret_cast<double*>(sb + S.x2);
+  const int64_t npad = L.npad;
+  cudaError_t e = cudaMemsetAsync(info_dev, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess) return fail_cuda("memset info", e);
+  int rc = run_warp(gp, theta_dev, 1, W, npad, st);
+  if (rc) return rc;
+  rc = run_cov(gp, theta_dev, 1, W, npad, W.kl, st);
+  if (rc) return rc;
+  rc = run_factor(gp, 1, W.kl, W.t, info_dev, npad, true, st);
+  if (rc) return rc;
+  rc = run_trsv_alpha(gp, 1, W, npad, true, st);
+  if (rc) return rc;
+  hyp_store_kernel<<<1, 128, 0, st>>>(gp->kd, theta_dev, reinterpret_cast<HypS*>(sb + S.hyp));
+  LAUNCH_CHECK("hyp_store_kernel");
+  return 0;
+}
+
+static const int64_t kPanelCols = 148 * 64 * 2;  // test points per K_xs panel
+
+extern "C" size_t avn_gp_predict_workspace_bytes(const avn_gp* gp, int64_t M) {
+  if (!gp || gp->N < 1 || M < 1) return 0;
+  const int64_t npad = npad_of(gp->N);
+  int64_t cols = align_up(M < kPanelCols ? M : kPanelCols, TILE);
+  return (size_t)(npad * cols * 8);
+}
+
+extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* Xs_dev, int64_t M,
+                              const avn_epilogue* epi, const double* mean_add_dev, double* out_mean_dev,
+                              double* out_var_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!gp || !state_dev || !Xs_dev || !epi || !out_mean_dev || !out_var_dev || !ws_dev)
+    return fail("avn_gp_predict: null argument");
+  if (gp->N < 1) return fail("avn_gp_predict: set_data first");
+  if (M < 1) return fail("avn_gp_predict: M must be >= 1");
+  if (epi->mode < 0 || epi->mode > 2) return fail("avn_gp_predict: bad epilogue mode");
+  if (epi->mode != 0 && (epi->deg < 1 || epi->deg > AVN_MAX_GH)) return fail("avn_gp_predict: deg out of range [1,32]");
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = npad_of(gp->N);
+  StateLayout S = state_layout(gp);
+  const int64_t cols_cap = (int64_t)(ws_bytes / (npad * 8)) / TILE * TILE;
+  if (cols_cap < TILE) return fail("avn_gp_predict: workspace too small");
+  gp->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* sb = static_cast<const char*>(state_dev);
+  const HypS* hyp = reinterpret_cast<const HypS*>(sb + S.hyp);
+  const double* alpha = reinterpret_cast<const double*>(sb + S.alpha);
+  const double* xs = reinterpret_cast<const double*>(sb + S.xs);
+  const double* x2 = reinterpret_cast<const double*>(sb + S.x2);
+  const double* T = reinterpret_cast<const double*>(sb + S.t);
+  double* Kxs = static_cast<double*>(ws_dev);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = opt_in_smem(predict_var_kernel, PredG::SMEM_BYTES);
+    if (e != cudaSuccess) return fail_cuda("predict smem opt-in", e);
+    attr_done = true;
+  }
+  const size_t smem_kxs = (size_t)(kd.nkern * TILE * (kd.d | 1) + kd.nkern * TILE) * 8;
+  for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
+    const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
+    const unsigned nblk = (unsigned)(cols / TILE);
+    kxs_kernel<<<nblk, 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols,
+                                            Kxs, out_mean_dev);
+    LAUNCH_CHECK("kxs_kernel");
+    predict_var_kernel<<<nblk, PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0,
+                                                                         *epi, mean_add_dev, out_mean_dev, out_var_dev);
+    LAUNCH_CHECK("predict_var_kernel");
+  }
+  return 0;
+}

@@ -1,0 +1,827 @@
+// Kernels of the GP inner loop (sm_100a).  Layout conventions:
+//   * every N x N matrix of a hyperparameter sample b is stored row-major in a padded
+//     [npad][npad] slab (npad = N rounded up to 64), lower block-triangle valid; padding rows/cols
+//     carry the identity so that L, T = L^-1 stay block-diag(., I) and no kernel needs ragged tiles;
+//   * the batch dimension is the slowest one; blockIdx.y (or .x for per-sample kernels) = b.
+#pragma once
+#include "avn_dev.cuh"
+#include "tile_gemm.cuh"
+#include "warp.cuh"
+
+namespace avn {
+
+struct WsPtrs {
+  double* xw;      // [B][npad][d]            warped inputs
+  double* dxw;     // [B][npad][d][MAXWP]     d warped input / d warp params (only with learnable x warps)
+  double* xs;      // [B][nkern][npad][d]     inputs scaled by 1/l of each kernel
+  double* x2;      // [B][nkern][npad]        row norms of xs (NumPy summation order)
+  double* z;       // [B][npad]               converted outputs
+  double* dz;      // [B][npad][MAXWP]        d z / d output-warp params
+  double* wstat;   // [B][16]                 0: sum log g'; 1..8: its param derivatives; 9: quad; 10: logdet
+  double* kl;      // [B][npad][npad]         K then L
+  double* t;       // [B][npad][npad]         T = L^-1
+  double* beta;    // [B][npad]
+  double* alpha;   // [B][npad]
+  double* gpart;   // [B][ntiles][MAXACC]     per-tile partial sums of the gradient contraction
+  double* gxpart;  // [B][nb][npad][d]        per-source-tile partial sums of d ll / d warped input
+};
+
+constexpr int WSTAT = 16;
+
+// ------------------------------------------------------------------------------------------------
+// K0: conversions.  One CTA per hyperparameter sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs, const double* __restrict__ X,
+                                                   const double* __restrict__ y, int N, int npad,
+                                                   const double* __restrict__ theta, WsPtrs ws) {
+  __shared__ double sh[128];
+  __shared__ HypS hyp;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const double* th = theta + (int64_t)b * kd.P;
+  load_hyp(hyp, kd, th);
+  double* xw = ws.xw + (int64_t)b * npad * kd.d;
+  for (int e = tid; e < npad * kd.d; e += nt) xw[e] = (e / kd.d < N) ? X[e] : 0.0;
+  __syncthreads();
+  int poff = 0;
+  for (int m = 0; m < kd.d; m++) {
+    const avn_warp_prog& pr = progs.xw[m];
+    if (pr.nstages > 0) {
+      double dummy = 0, ddummy[MAXWP];
+      double* dual = ws.dxw + ((int64_t)b * npad * kd.d + m) * MAXWP;
+      run_warp_column(pr, th + kd.off_iw + poff, N, xw + m, kd.d, dual, (int64_t)kd.d * MAXWP, 0, dummy, ddummy, sh);
+      poff += pr.nparams;
+    }
+  }
+  double* z = ws.z + (int64_t)b * npad;
+  for (int n = tid; n < npad; n += nt) z[n] = (n < N) ? y[n] : 0.0;
+  __syncthreads();
+  double* wst = ws.wstat + (int64_t)b * WSTAT;
+  if (progs.yw.nstages > 0) {
+    double lsum = 0, dlsum[MAXWP];
+    for (int q = 0; q < MAXWP; q++) dlsum[q] = 0.0;
+    run_warp_column(progs.yw, th + kd.off_cw, N, z, 1, ws.dz + (int64_t)b * npad * MAXWP, MAXWP, 1, lsum, dlsum, sh);
+    double tot = block_sum(lsum, sh);
+    if (tid == 0) wst[0] = tot;
+    for (int q = 0; q < progs.yw.nparams; q++) {
+      double tq = block_sum(dlsum[q], sh);
+      if (tid == 0) wst[1 + q] = tq;
+    }
+  } else if (tid == 0) {
+    wst[0] = 0.0;
+  }
+  __syncthreads();
+  // scaled copies and row norms per kernel (X * (1/ls); sum(square(.), 1))
+  for (int k = 0; k < kd.nkern; k++) {
+    double* xs = ws.xs + ((int64_t)b * kd.nkern + k) * npad * kd.d;
+    double* x2 = ws.x2 + ((int64_t)b * kd.nkern + k) * npad;
+    for (int e = tid; e < npad * kd.d; e += nt) xs[e] = __dmul_rn(xw[e], hyp.invl[k][e % kd.d]);
+    __syncthreads();
+    for (int n = tid; n < npad; n += nt) x2[n] = sumsq_numpy_order(xs + (int64_t)n * kd.d, kd.d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: covariance build, lower 64x64 tiles, batched.  grid (ntiles_lower, B), 256 threads.
+// Writes K + (gv + jitter) I; padding rows/cols carry the identity.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tri_index(int t, int& i, int& j) {
+  i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((i + 1) * (i + 2) / 2 <= t) i++;
+  while (i * (i + 1) / 2 > t) i--;
+  j = t - i * (i + 1) / 2;
+}
+
+__global__ void __launch_bounds__(256) cov_kernel(KernDesc kd, int N, int npad, const double* __restrict__ theta,
+                                                  const double* __restrict__ xs_all, const double* __restrict__ x2_all,
+                                                  double* __restrict__ Kout) {
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  int ti, tj;
+  tri_index(blockIdx.x, ti, tj);
+  const int i0 = ti * TILE, j0 = tj * TILE;
+  const int d = kd.d, nk = kd.nkern;
+  load_hyp(hyp, kd, theta + (int64_t)b * kd.P);
+  // smem: xi[nk][64][d], xj[nk][64][d], x2i[nk][64], x2j[nk][64]
+  double* sxi = smem;
+  double* sxj = sxi + nk * TILE * d;
+  double* s2i = sxj + nk * TILE * d;
+  double* s2j = s2i + nk * TILE;
+  for (int k = 0; k < nk; k++) {
+    const double* xs = xs_all + ((int64_t)b * nk + k) * npad * d;
+    const double* x2 = x2_all + ((int64_t)b * nk + k) * npad;
+    for (int e = tid; e < TILE * d; e += 256) {
+      sxi[k * TILE * d + e] = xs[(int64_t)i0 * d + e];
+      sxj[k * TILE * d + e] = xs[(int64_t)j0 * d + e];
+    }
+    if (tid < TILE) {
+      s2i[k * TILE + tid] = x2[i0 + tid];
+      s2j[k * TILE + tid] = x2[j0 + tid];
+    }
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double* Kb = Kout + (int64_t)b * npad * npad;
+  const double dadd = hyp.gv + kd.jitter;
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int r = ty * 4 + rr, I = i0 + r;
+    double out[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      const int c = tx * 4 + cc, J = j0 + c;
+      double v;
+      if (I >= N || J >= N) {
+        v = (I == J) ? 1.0 : 0.0;
+      } else {
+        v = cov_fold(kd, hyp, sxi + r * d, TILE * d, s2i + r, TILE, sxj + c * d, TILE * d, s2j + c, TILE);
+        if (I == J) v += dadd;
+      }
+      out[cc] = v;
+    }
+    double2* dst = reinterpret_cast<double2*>(Kb + (int64_t)I * npad + j0 + tx * 4);
+    dst[0] = make_double2(out[0], out[1]);
+    dst[1] = make_double2(out[2], out[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: blocked left-looking Cholesky, one launch triple per 64-wide block column k:
+//   potrf_update : A[i,k] -= sum_{j<k} L[i,j] L[k,j]^T          (DMMA, i >= k)
+//   potrf_diag   : L[k,k] = chol(A[k,k]);  T[k,k] = L[k,k]^-1    (shared memory, one CTA per sample)
+//   potrf_panel  : L[i,k] = A[i,k] T[k,k]^T                      (DMMA, i > k)
+// ------------------------------------------------------------------------------------------------
+template <int BM>
+struct PotrfCfg {
+  using G = TileGemm<BM, 64, 16, 32, 32, 4, false, false>;
+};
+
+template <int BM>
+__global__ void __launch_bounds__(PotrfCfg<BM>::G::NTHREADS) potrf_update_kernel(double* __restrict__ Lall, int npad,
+                                                                                  int kblk) {
+  using G = typename PotrfCfg<BM>::G;
+  extern __shared__ double smem[];
+  const int b = blockIdx.y;
+  double* L = Lall + (int64_t)b * npad * npad;
+  const int r0 = kblk * TILE + blockIdx.x * BM;
+  const int rows = min(BM, npad - r0);
+  G g;
+  g.zero();
+  g.run(smem, L + (int64_t)r0 * npad, npad, rows, L + (int64_t)kblk * TILE * npad, npad, 64, kblk * TILE);
+  double* C = L + (int64_t)r0 * npad + kblk * TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < G::MI; i++)
+#pragma unroll
+    for (int j = 0; j < G::NI; j++) {
+      int r = wm * G::WM + i * 8 + gq, c = wn * G::WN + j * 8 + 2 * t;
+      if (r < rows) {
+        double2* p = reinterpret_cast<double2*>(C + (int64_t)r * npad + c);
+        double2 v = *p;
+        v.x -= g.acc[i][j][0];
+        v.y -= g.acc[i][j][1];
+        *p = v;
+      }
+    }
+}
+
+template <int BM>
+__global__ void __launch_bounds__(PotrfCfg<BM>::G::NTHREADS) potrf_panel_kernel(double* __restrict__ Lall,
+                                                                                 const double* __restrict__ Tall,
+                                                                                 int npad, int kblk) {
+  using G = typename PotrfCfg<BM>::G;
+  extern __shared__ double smem[];
+  const int b = blockIdx.y;
+  double* L = Lall + (int64_t)b * npad * npad;
+  const double* T = Tall + (int64_t)b * npad * npad;
+  const int r0 = (kblk + 1) * TILE + blockIdx.x * BM;
+  const int rows = min(BM, npad - r0);
+  G g;
+  g.zero();
+  double* A = L + (int64_t)r0 * npad + kblk * TILE;
+  g.run(smem, A, npad, rows, T + (int64_t)kblk * TILE * npad + kblk * TILE, npad, 64, TILE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < G::MI; i++)
+#pragma unroll
+    for (int j = 0; j < G::NI; j++) {
+      int r = wm * G::WM + i * 8 + gq, c = wn * G::WN + j * 8 + 2 * t;
+      if (r < rows)
+        *reinterpret_cast<double2*>(A + (int64_t)r * npad + c) = make_double2(g.acc[i][j][0], g.acc[i][j][1]);
+    }
+}
+
+// diagonal block: unblocked Cholesky + triangular inverse in shared memory.  grid (B), 256 threads.
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lall, double* __restrict__ Tall,
+                                                         int npad, int kblk, int32_t* __restrict__ info) {
+  constexpr int LD = TILE + 1;
+  extern __shared__ double smem[];
+  double* A = smem;
+  double* Ti = smem + TILE * LD;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* Lkk = Lall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
+  double* Tkk = Tall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
+  for (int e = tid; e < TILE * TILE; e += 256) {
+    int i = e >> 6, c = e & 63;
+    A[i * LD + c] = (c <= i) ? Lkk[(int64_t)i * npad + c] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < TILE; j++) {
+    double dj = A[j * LD + j];
+    if (!(dj > 0.0)) {  // also catches NaN
+      if (tid == 0 && info[b] == 0) info[b] = kblk * TILE + j + 1;
+      dj = 1.0;
+    }
+    const double ljj = sqrt(dj);
+    const double inv = 1.0 / ljj;
+    __syncthreads();
+    if (tid < TILE) {
+      if (tid == j) A[j * LD + j] = ljj;
+      else if (tid > j) A[tid * LD + j] *= inv;
+    }
+    __syncthreads();
+    // trailing update of the lower triangle right of column j
+    const int rem = TILE - 1 - j;  // rows/cols j+1 .. 63
+    for (int e = tid; e < rem * rem; e += 256) {
+      int i = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= i) A[i * LD + c] -= A[i * LD + j] * A[c * LD + j];
+    }
+    __syncthreads();
+  }
+  // T = L^-1: 4 threads per column c split the dot products
+  {
+    const int c = tid >> 2, part = tid & 3;
+    for (int i = 0; i < TILE; i++) {
+      // all threads walk rows together; x[i] depends on x[c..i-1] written in earlier iterations
+      double s = 0.0;
+      if (i > c)
+        for (int k = c + part; k < i; k += 4) s += A[i * LD + k] * Ti[k * LD + c];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0) {
+        double v;
+        if (i < c) v = 0.0;
+        else if (i == c) v = 1.0 / A[i * LD + i];
+        else v = -s / A[i * LD + i];
+        Ti[i * LD + c] = v;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < TILE * TILE; e += 256) {
+    int i = e >> 6, c = e & 63;
+    Lkk[(int64_t)i * npad + c] = (c <= i) ? A[i * LD + c] : 0.0;
+    Tkk[(int64_t)i * npad + c] = Ti[i * LD + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// beta = L^-1 z by blocked forward substitution (diagonal blocks through T[k,k]), plus the two
+// scalars of the log-likelihood:  quad = beta^T beta,  logdet = sum log L_ii.   grid (B), 256 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ Lall, const double* __restrict__ Tall,
+                                                   const double* __restrict__ zall, int npad,
+                                                   double* __restrict__ beta_all, double* __restrict__ wstat) {
+  extern __shared__ double sbeta[];  // npad + 64 + 32
+  double* rt = sbeta + npad;
+  double* red = rt + TILE;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* L = Lall + (int64_t)b * npad * npad;
+  const double* T = Tall + (int64_t)b * npad * npad;
+  const double* z = zall + (int64_t)b * npad;
+  const int nb = npad / TILE;
+  const int row = tid >> 2, part = tid & 3;
+  double logdet = 0.0;
+  for (int k = 0; k < nb; k++) {
+    const double* Lr = L + (int64_t)(k * TILE + row) * npad;
+    double s = 0.0;
+    for (int j = part * 4; j < k * TILE; j += 16) {
+      const double2 a0 = *reinterpret_cast<const double2*>(Lr + j);
+      const double2 a1 = *reinterpret_cast<const double2*>(Lr + j + 2);
+      s += a0.x * sbeta[j] + a0.y * sbeta[j + 1] + a1.x * sbeta[j + 2] + a1.y * sbeta[j + 3];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0) rt[row] = z[k * TILE + row] - s;
+    __syncthreads();
+    if (tid < TILE) {
+      const double* Tr = T + (int64_t)(k * TILE + tid) * npad + k * TILE;
+      double acc = 0.0;
+      for (int c = 0; c <= tid; c++) acc += Tr[c] * rt[c];
+      sbeta[k * TILE + tid] = acc;
+      logdet += log(L[(int64_t)(k * TILE + tid) * npad + k * TILE + tid]);
+    }
+    __syncthreads();
+  }
+  double q = 0.0;
+  for (int n = tid; n < npad; n += 256) {
+    double v = sbeta[n];
+    beta_all[(int64_t)b * npad + n] = v;
+    q += v * v;
+  }
+  double quad = block_sum(q, red);
+  double ld = block_sum(logdet, red);
+  if (tid == 0) {
+    wstat[(int64_t)b * WSTAT + 9] = quad;
+    wstat[(int64_t)b * WSTAT + 10] = ld;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: T = L^-1, block row i:  T[i,j] = -T[i,i] * sum_{k=j}^{i-1} L[i,k] T[k,j]   (j < i)
+// grid (i, B): one 64x64 output tile per CTA, 128 threads.
+// ------------------------------------------------------------------------------------------------
+using TrtriG = TileGemm<64, 64, 16, 32, 32, 4, false, true>;
+
+template <int LDA, int LDB>
+__device__ __forceinline__ void smem_gemm64(double (&acc)[4][4][2], const double* sA,
+                                            const double* sB, int wm, int wn, int g, int t) {
+  // acc(m,n) += sum_k sA[m][k] * sB[k][n], 64x64x64, warp tile 32x32
+#pragma unroll 4
+  for (int kk = 0; kk < 64; kk += 4) {
+    double a[4], bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = sA[(wm * 32 + i * 8 + g) * LDA + kk + t];
+#pragma unroll
+    for (int j = 0; j < 4; j++) bb[j] = sB[(kk + t) * LDB + wn * 32 + j * 8 + g];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+  }
+}
+
+__global__ void __launch_bounds__(TrtriG::NTHREADS) trtri_row_kernel(const double* __restrict__ Lall,
+                                                                     double* __restrict__ Tall, int npad, int iblk) {
+  using G = TrtriG;
+  constexpr int LDS = TILE + SPAD;
+  extern __shared__ double smem[];
+  const int b = blockIdx.y, jblk = blockIdx.x;
+  const double* L = Lall + (int64_t)b * npad * npad;
+  double* T = Tall + (int64_t)b * npad * npad;
+  const int i0 = iblk * TILE, j0 = jblk * TILE;
+  G g;
+  g.zero();
+  g.run(smem, L + (int64_t)i0 * npad + j0, npad, 64, T + (int64_t)j0 * npad + j0, npad, 64, i0 - j0);
+  // S -> smem as [k][n]; T[i,i] -> smem as [m][k]
+  double* sS = smem;
+  double* sT = smem + TILE * LDS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < G::MI; i++)
+#pragma unroll
+    for (int j = 0; j < G::NI; j++) {
+      int r = wm * G::WM + i * 8 + gq, c = wn * G::WN + j * 8 + 2 * t;
+      sS[r * LDS + c] = g.acc[i][j][0];
+      sS[r * LDS + c + 1] = g.acc[i][j][1];
+    }
+  const double* Tii = T + (int64_t)i0 * npad + i0;
+  for (int e = tid; e < TILE * TILE / 2; e += G::NTHREADS) {
+    int r = e / (TILE / 2), c = (e % (TILE / 2)) * 2;
+    double2 v = *reinterpret_cast<const double2*>(Tii + (int64_t)r * npad + c);
+    sT[r * LDS + c] = v.x;
+    sT[r * LDS + c + 1] = v.y;
+  }
+  __syncthreads();
+  double acc2[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc2[i][j][0] = acc2[i][j][1] = 0.0;
+  smem_gemm64<LDS, LDS>(acc2, sT, sS, wm, wn, gq, t);
+  double* out = T + (int64_t)i0 * npad + j0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+      *reinterpret_cast<double2*>(out + (int64_t)r * npad + c) = make_double2(-acc2[i][j][0], -acc2[i][j][1]);
+    }
+}
+
+// alpha = T^T beta.  grid (nb, B), 256 threads.
+__global__ void __launch_bounds__(256) alpha_kernel(const double* __restrict__ Tall, const double* __restrict__ beta_all,
+                                                    int npad, double* __restrict__ alpha_all) {
+  __shared__ double part[4][TILE];
+  const int b = blockIdx.y, j0 = blockIdx.x * TILE, tid = threadIdx.x;
+  const int c = tid & 63, rg = tid >> 6;
+  const double* T = Tall + (int64_t)b * npad * npad;
+  const double* beta = beta_all + (int64_t)b * npad;
+  double acc = 0.0;
+  for (int i = j0 + rg; i < npad; i += 4) acc += T[(int64_t)i * npad + j0 + c] * beta[i];
+  part[rg][c] = acc;
+  __syncthreads();
+  if (tid < TILE)
+    alpha_all[(int64_t)b * npad + j0 + tid] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: K^-1 tiles (T^T T) fused with the gradient contraction  1/2 sum_ij W_ij dK_ij/dtheta,
+// W = alpha alpha^T - K^-1.  K^-1 is never written to memory.
+// grid (ntiles_lower, B), 128 threads; tile (i, j<=i):  Kinv[i,j] = sum_{k >= i} T[k,i]^T T[k,j].
+// ------------------------------------------------------------------------------------------------
+using KinvG = TileGemm<64, 64, 16, 32, 32, 4, true, true>;
+
+template <bool WITH_GX>
+__global__ void __launch_bounds__(KinvG::NTHREADS) kinv_grad_kernel(KernDesc kd, int N, int npad,
+                                                                    const double* __restrict__ theta,
+                                                                    const double* __restrict__ Tall,
+                                                                    const double* __restrict__ alpha_all,
+                                                                    const double* __restrict__ xw_all,
+                                                                    double* __restrict__ gpart,
+                                                                    double* __restrict__ gxpart) {
+  using G = KinvG;
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  __shared__ double wpart[4][MAXACC];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  int ti, tj;
+  tri_index(blockIdx.x, ti, tj);
+  const int i0 = ti * TILE, j0 = tj * TILE;
+  const int d = kd.d, nk = kd.nkern;
+  const double* T = Tall + (int64_t)b * npad * npad;
+  load_hyp(hyp, kd, theta + (int64_t)b * kd.P);
+  G g;
+  g.zero();
+  g.run(smem, T + (int64_t)i0 * npad + i0, npad, 64, T + (int64_t)i0 * npad + j0, npad, 64, npad - i0);
+  // stage x rows and alpha of both blocks (aliases the pipeline buffers, free after run())
+  const int ldx = d | 1;
+  double* sxi = smem;
+  double* sxj = sxi + TILE * ldx;
+  double* sai = sxj + TILE * ldx;
+  double* saj = sai + TILE;
+  double* sgr = saj + TILE;               // [2 (wn)][64][MAXD] row sums (WITH_GX), one owner lane per slot
+  double* sgc = sgr + 2 * TILE * MAXD;    // [2 (wm)][64][MAXD] col sums
+  const double* xw = xw_all + (int64_t)b * npad * d;
+  for (int e = tid; e < TILE * d; e += G::NTHREADS) {
+    int r = e / d, m = e % d;
+    sxi[r * ldx + m] = xw[(int64_t)(i0 + r) * d + m];
+    sxj[r * ldx + m] = xw[(int64_t)(j0 + r) * d + m];
+  }
+  if (tid < TILE) {
+    sai[tid] = alpha_all[(int64_t)b * npad + i0 + tid];
+    saj[tid] = alpha_all[(int64_t)b * npad + j0 + tid];
+  }
+  if (WITH_GX)
+    for (int e = tid; e < 4 * TILE * MAXD; e += G::NTHREADS) sgr[e] = 0.0;
+  for (int e = tid; e < 4 * MAXACC; e += G::NTHREADS) (&wpart[0][0])[e] = 0.0;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+  const double symw = (ti == tj) ? 1.0 : 2.0;
+  // W (weighted, masked) replaces the accumulators; trace part for d/d gv
+  double trw = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t + h;
+        int I = i0 + r, J = j0 + c;
+        double w = (I < N && J < N) ? (sai[r] * saj[c] - g.acc[i][j][h]) : 0.0;
+        if (I == J) trw += w;
+        g.acc[i][j][h] = w * symw;
+      }
+  const int slot_gv = nk * d + nk, slot_alpha = slot_gv + 1;
+  {
+    double s = warp_sum(trw);
+    if (lane == 0) wpart[warp][slot_gv] = s;
+  }
+  double wk[4][4][2];
+  for (int k = 0; k < nk; k++) {
+    double skv = 0.0, sal = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t + h;
+          // values of all kernels at this pair (direct differences), fold coefficient of kernel k
+          double vals[MAXK], kk_k = 0.0, dk_k = 0.0, r2_k = 0.0;
+          for (int q = 0; q < nk; q++) {
+            double r2 = 0.0;
+            for (int m = 0; m < d; m++) {
+              double s = (sxi[r * ldx + m] - sxj[c * ldx + m]) * hyp.invl[q][m];
+              r2 = fma(s, s, r2);
+            }
+            double kv_, dk_;
+            kern_val(kd.kern[q], r2, hyp.alpha, kv_, dk_);
+            vals[q] = hyp.kv[q] * kv_;
+            if (q == k) { kk_k = kv_; dk_k = dk_; r2_k = r2; }
+          }
+          // coef = dK/dvals[k] through the left-to-right fold
+          double coef = 1.0;
+          {
+            double pref = vals[0];
+            double prefs[MAXK];
+            prefs[0] = pref;
+            for (int q = 1; q < nk; q++) {
+              pref = (kd.op[q - 1] == AVN_ADD) ? pref + vals[q] : pref * vals[q];
+              prefs[q] = pref;
+            }
+            double gg = 1.0;
+            for (int q = nk - 1; q >= 1; q--) {
+              if (kd.op[q - 1] == AVN_ADD) {
+                if (q == k) coef = gg;
+              } else {
+                if (q == k) coef = gg * prefs[q - 1];
+                gg *= vals[q];
+              }
+            }
+            if (k == 0) coef = gg;
+          }
+          double w = g.acc[i][j][h] * coef;
+          skv += w * kk_k;
+          wk[i][j][h] = w * hyp.kv[k] * dk_k;
+          if (kd.kern[k] == AVN_RATQUAD) {
+            double base = 1.0 + 0.5 * r2_k / hyp.alpha;
+            double kq = pow(base, -hyp.alpha);
+            sal += w * hyp.kv[k] * kq * (-log(base) + (0.5 * r2_k / hyp.alpha) / base);
+          }
+        }
+    {
+      double s = warp_sum(skv);
+      if (lane == 0) wpart[warp][nk * d + k] = s;
+      if (kd.kern[k] == AVN_RATQUAD) {
+        double s2 = warp_sum(sal);
+        if (lane == 0) wpart[warp][slot_alpha] = s2;
+      }
+    }
+    for (int m = 0; m < d; m++) {
+      const double il = hyp.invl[k][m];
+      double xi[4], xj[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) xi[i] = sxi[(wm * 32 + i * 8 + gq) * ldx + m];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        xj[j][0] = sxj[(wn * 32 + j * 8 + 2 * t) * ldx + m];
+        xj[j][1] = sxj[(wn * 32 + j * 8 + 2 * t + 1) * ldx + m];
+      }
+      double s2 = 0.0;
+      double rs[4] = {0, 0, 0, 0}, cs[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            double s = (xi[i] - xj[j][h]) * il;
+            double ws_ = wk[i][j][h] * s;
+            s2 = fma(ws_, s, s2);
+            if (WITH_GX) {
+              rs[i] += ws_;
+              cs[j][h] += ws_;
+            }
+          }
+      s2 = warp_sum(s2);
+      if (lane == 0) wpart[warp][k * d + m] = s2;
+      if (WITH_GX) {
+        // d ll / d xw[I][m] += 2 * invl * sum_J (W K')_IJ s_IJ ; the symmetric weight is removed again
+        const double f = 2.0 * il / symw;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          double v = rs[i];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if (t == 0) sgr[(wn * TILE + wm * 32 + i * 8 + gq) * MAXD + m] += v * f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            double v = cs[j][h];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (gq == 0) sgc[(wm * TILE + wn * 32 + j * 8 + 2 * t + h) * MAXD + m] -= v * f;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  const int nacc = nk * d + nk + 2;
+  const int64_t ntiles = gridDim.x;
+  double* gp = gpart + ((int64_t)b * ntiles + blockIdx.x) * MAXACC;
+  for (int e = tid; e < nacc; e += G::NTHREADS) gp[e] = (wpart[0][e] + wpart[1][e]) + (wpart[2][e] + wpart[3][e]);
+  if (WITH_GX) {
+    const int nb = npad / TILE;
+    // rows of block i take this tile's row sums (source tj); rows of block j take its column sums (source ti)
+    double* gr = gxpart + (((int64_t)b * nb + tj) * npad + i0) * d;
+    for (int e = tid; e < TILE * d; e += G::NTHREADS)
+      gr[e] = sgr[(e / d) * MAXD + e % d] + sgr[(TILE + e / d) * MAXD + e % d];
+    if (ti != tj) {
+      double* gc = gxpart + (((int64_t)b * nb + ti) * npad + j0) * d;
+      for (int e = tid; e < TILE * d; e += G::NTHREADS)
+        gc[e] = sgc[(e / d) * MAXD + e % d] + sgc[(TILE + e / d) * MAXD + e % d];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalisation: ll and gradient assembly.  grid (B), 256 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs progs, int N, int npad, int ntiles,
+                                                       int want_grad, const double* __restrict__ theta, WsPtrs ws,
+                                                       const int32_t* __restrict__ info, double* __restrict__ ll,
+                                                       double* __restrict__ grad) {
+  __shared__ double slots[MAXACC];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* th = theta + (int64_t)b * kd.P;
+  const double* wst = ws.wstat + (int64_t)b * WSTAT;
+  const bool bad = info[b] != 0;
+  if (tid == 0) {
+    const double norm = -0.5 * N * 1.8378770664093454835606594728112;  // log(2 pi)
+    double v = (norm - 0.5 * wst[9]) - wst[10] + wst[0];
+    ll[b] = bad ? -INFINITY : v;
+  }
+  if (!want_grad) return;
+  double* gr = grad + (int64_t)b * kd.P;
+  if (bad) {
+    for (int e = tid; e < kd.P; e += 256) gr[e] = 0.0;
+    return;
+  }
+  const int d = kd.d, nk = kd.nkern;
+  const int nacc = nk * d + nk + 2;
+  for (int e = tid; e < nacc; e += 256) {
+    double s = 0.0;
+    const double* gp = ws.gpart + (int64_t)b * ntiles * MAXACC + e;
+    for (int tI = 0; tI < ntiles; tI++) s += gp[(int64_t)tI * MAXACC];
+    slots[e] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < nk * d; e += 256) gr[kd.off_l + e] = -slots[e] / th[kd.off_l + e];
+  if (tid < nk) gr[kd.off_kv + tid] = 0.5 * slots[nk * d + tid];
+  if (tid == 0) {
+    if (kd.noise) gr[kd.off_gv] = 0.5 * slots[nk * d + nk];
+    if (kd.has_alpha) gr[kd.off_alpha] = 0.5 * slots[nk * d + nk + 1];
+  }
+  // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p.  One warp per (dimension, parameter)
+  // pair: lanes stride over n, one shuffle reduction, no block-level barrier.
+  const int warp = tid >> 5, lane = tid & 31;
+  if (kd.n_iw > 0) {
+    const int nb = npad / TILE;
+    int poff = 0;
+    for (int m = 0; m < d; m++) {
+      const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;
+      for (int q = warp; q < np; q += 8) {
+        double acc = 0.0;
+        for (int n = lane; n < N; n += 32) {
+          double gsum = 0.0;
+          for (int s = 0; s < nb; s++) gsum += ws.gxpart[(((int64_t)b * nb + s) * npad + n) * d + m];
+          acc += gsum * ws.dxw[(((int64_t)b * npad + n) * d + m) * MAXWP + q];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) gr[kd.off_iw + poff + q] = acc;
+      }
+      poff += np;
+    }
+  }
+  // learnable output warp: -alpha^T dz/dp + sum d log g'/dp
+  if (kd.n_cw > 0) {
+    const double* al = ws.alpha + (int64_t)b * npad;
+    for (int q = warp; q < kd.n_cw; q += 8) {
+      double acc = 0.0;
+      for (int n = lane; n < N; n += 32) acc += al[n] * ws.dz[((int64_t)b * npad + n) * MAXWP + q];
+      acc = warp_sum(acc);
+      if (lane == 0) gr[kd.off_cw + q] = -acc + wst[1 + q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: predict.  (a) cross-covariance panel K_xs [npad][mld] + latent mean  mu = K_xs^T alpha
+//               (b) V = T K_xs by DMMA row tile by row tile, column sums of V^2, variance,
+//                   Gauss-Hermite reversion / EI epilogue (gpmcmc.py:545-569).
+// ------------------------------------------------------------------------------------------------
+struct PredState {
+  // layout of the state buffer produced by factorize (all offsets in doubles from the base)
+  int64_t off_alpha, off_xs, off_x2, off_t, off_hyp;
+};
+
+__global__ void __launch_bounds__(256) kxs_kernel(KernDesc kd, int N, int npad, const HypS* __restrict__ hyp_g,
+                                                  const double* __restrict__ xs_tr, const double* __restrict__ x2_tr,
+                                                  const double* __restrict__ alpha, const double* __restrict__ Xtest,
+                                                  int64_t M, int64_t m_begin, int mld, double* __restrict__ Kxs,
+                                                  double* __restrict__ mu) {
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  __shared__ double part[4][TILE];
+  const int tid = threadIdx.x, c = tid & 63, rg = tid >> 6;
+  const int d = kd.d, nk = kd.nkern;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;  // column inside the panel
+  const int64_t mg = m_begin + col0 + c;            // global test index
+  for (int e = tid; e < (int)(sizeof(HypS) / sizeof(double)); e += 256)
+    reinterpret_cast<double*>(&hyp)[e] = reinterpret_cast<const double*>(hyp_g)[e];
+  __syncthreads();
+  const int ldx = d | 1;
+  double* sx = smem;                 // [nk][64][ldx] scaled test points
+  double* sx2 = sx + nk * TILE * ldx;  // [nk][64]
+  if (rg == 0) {
+    for (int k = 0; k < nk; k++) {
+      double tmp[MAXD];
+      for (int m = 0; m < d; m++) {
+        double x = (mg < M) ? Xtest[mg * d + m] : 0.0;
+        tmp[m] = __dmul_rn(x, hyp.invl[k][m]);
+        sx[(k * TILE + c) * ldx + m] = tmp[m];
+      }
+      sx2[k * TILE + c] = sumsq_numpy_order(tmp, d);
+    }
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int n = rg; n < npad; n += 4) {
+    double v = 0.0;
+    if (n < N)
+      v = cov_fold(kd, hyp, xs_tr + (int64_t)n * d, (int64_t)npad * d, x2_tr + n, npad, sx + c * ldx, TILE * ldx,
+                   sx2 + c, TILE);
+    Kxs[(int64_t)n * mld + col0 + c] = v;
+    acc = fma(v, alpha[n], acc);
+  }
+  part[rg][c] = acc;
+  __syncthreads();
+  if (tid < TILE && m_begin + col0 + tid < M)
+    mu[m_begin + col0 + tid] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+}
+
+using PredG = TileGemm<64, 64, 16, 32, 32, 4, false, true>;
+
+__global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc kd, int npad,
+                                                                      const HypS* __restrict__ hyp_g,
+                                                                      const double* __restrict__ T,
+                                                                      const double* __restrict__ Kxs, int mld,
+                                                                      int64_t M, int64_t m_begin, avn_epilogue epi,
+                                                                      const double* __restrict__ mean_add,
+                                                                      double* __restrict__ mu_io,
+                                                                      double* __restrict__ var_out) {
+  using G = PredG;
+  extern __shared__ double smem[];
+  __shared__ double colsq[2][TILE];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int nb = npad / TILE;
+  double cs[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  G g;
+  for (int ib = 0; ib < nb; ib++) {
+    g.zero();
+    g.run(smem, T + (int64_t)ib * TILE * npad, npad, 64, Kxs + col0, mld, 64, (ib + 1) * TILE);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cs[j][0] = fma(g.acc[i][j][0], g.acc[i][j][0], cs[j][0]);
+        cs[j][1] = fma(g.acc[i][j][1], g.acc[i][j][1], cs[j][1]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      double v = cs[j][h];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (gq == 0) colsq[wm][wn * 32 + j * 8 + 2 * t + h] = v;
+    }
+  __syncthreads();
+  if (tid < TILE) {
+    const int64_t mg = m_begin + col0 + tid;
+    if (mg < M) {
+      const HypS& hyp = *hyp_g;
+      double kd_tot = kdiag_total(kd, hyp);
+      double var = kd_tot - (colsq[0][tid] + colsq[1][tid]);
+      var += hyp.gv;
+      double mu = mu_io[mg];
+      if (epi.mode != 0) {
+        const double madd = mean_add ? mean_add[mg] : 0.0;
+        const double sd = sqrt(2.0 * var);
+        double s1 = 0.0, s2 = 0.0;
+        for (int q = 0; q < epi.deg; q++) {
+          double yi = sd * epi.nodes[q] + mu;
+          double yr = prog_rev_const(epi.yrev, yi) + madd;
+          double f = yr;
+          if (epi.mode == 2) {
+            double df = epi.ei_max ? (yr - epi.yopt) : (epi.yopt - yr);
+            f = df > 0.0 ? df : 0.0;
+          }
+          s1 += epi.weights[q] * f;
+          s2 += epi.weights[q] * (yr * yr);
+        }
+        const double ispi = 0.56418958354775628694807945156077;  // 1/sqrt(pi)
+        mu = ispi * s1;
+        var = ispi * s2 - mu * mu;
+        if (epi.normvar) var /= mu * mu;
+      }
+      mu_io[mg] = mu;
+      var_out[mg] = var;
+    }
+  }
+}
+
+}  // namespace avn

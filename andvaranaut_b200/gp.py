@@ -1,0 +1,260 @@
+"""Device-side GP engine: thin Python object over the C ABI (``include/avn_gp.h``).
+
+PyTorch is used for device memory, streams and (in ``dist.py``) the process group only; all
+arithmetic happens in ``libavn_gp.so``.  One :class:`GPEngine` corresponds to one PyMC model of the
+reference (``pm.Model()`` built in ``GPMCMC.__fit``, andvaranaut/gpmcmc.py:185-323): a kernel fold,
+a noise flag, optional learnable input/output warps and the training data.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KERNEL_IDS, OP_IDS
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class GPError(RuntimeError):
+    pass
+
+
+class GPEngine:
+    def __init__(self, nx, kerns=('RBF',), ops=(), noise=True, jitter=1e-6, xwarps=None, ywarp=None,
+                 device=None):
+        """xwarps: per input dimension ``None`` or a list of stage tuples (``wgp.program()``);
+        ywarp: ``None`` or a list of stage tuples."""
+        if not torch.cuda.is_available():
+            raise GPError('GPEngine needs a CUDA device: there is no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        kerns = list(kerns)
+        ops = list(ops)
+        if len(ops) != len(kerns) - 1:
+            raise ValueError('need one op between each pair of kernels')
+        self.nx, self.kerns, self.ops, self.noise, self.jitter = nx, kerns, ops, bool(noise), float(jitter)
+        desc = _lib.ModelDesc()
+        desc.d = nx
+        desc.nkern = len(kerns)
+        for i, k in enumerate(kerns):
+            desc.kern[i] = KERNEL_IDS[k]
+        for i, o in enumerate(ops):
+            desc.op[i] = OP_IDS[o]
+        desc.noise = 1 if noise else 0
+        desc.jitter = jitter
+        self.n_iw = 0
+        if xwarps is not None:
+            if len(xwarps) != nx:
+                raise ValueError('xwarps must have one entry per input dimension')
+            for m, prog in enumerate(xwarps):
+                if prog:
+                    desc.xwarp[m] = _lib.make_prog(prog)
+                    self.n_iw += desc.xwarp[m].nparams
+        self.n_cw = 0
+        if ywarp:
+            desc.ywarp = _lib.make_prog(ywarp)
+            self.n_cw = desc.ywarp.nparams
+        self._desc = desc
+        h = C.c_void_p()
+        rc = self.lib.avn_gp_create(C.byref(desc), C.byref(h))
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self._h = h
+        self.P = self.lib.avn_gp_num_params(h)
+        self.N = 0
+        self._X = self._y = None
+        self._ws = None
+        self._state = None
+        self._pws = None
+        self.launches = 0
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            try:
+                self.lib.avn_gp_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- layout helpers ----------------------------------------------------------------------
+    def offsets(self):
+        o, p = {}, 0
+        if self.noise:
+            o['gv'] = p
+            p += 1
+        o['l'] = p
+        p += self.nx * len(self.kerns)
+        o['kv'] = p
+        p += len(self.kerns)
+        o['iw'] = p
+        p += self.n_iw
+        o['cw'] = p
+        p += self.n_cw
+        if 'RatQuad' in self.kerns:
+            o['alpha'] = p
+            p += 1
+        o['P'] = p
+        return o
+
+    def _dev(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.float64).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+
+    def set_data(self, X, y):
+        X = self._dev(X)
+        y = self._dev(y).reshape(-1)
+        if X.ndim != 2 or X.shape[1] != self.nx or X.shape[0] != y.shape[0]:
+            raise ValueError('X must be [N,nx] and y [N]')
+        self._X, self._y, self.N = X, y, X.shape[0]
+        rc = self.lib.avn_gp_set_data(self._h, _ptr(X), _ptr(y), self.N)
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self._state = None
+
+    @property
+    def npad(self):
+        return (self.N + _lib.AVN_TILE - 1) // _lib.AVN_TILE * _lib.AVN_TILE
+
+    def _workspace(self, B):
+        need = self.lib.avn_gp_workspace_bytes(self._h, B)
+        if need == 0:
+            raise GPError('set_data first')
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def max_batch(self, budget_bytes):
+        """largest B whose loglik workspace fits in ``budget_bytes``."""
+        per = self.lib.avn_gp_workspace_bytes(self._h, 1)
+        return max(1, int(budget_bytes // per))
+
+    # -- hot path ----------------------------------------------------------------------------
+    def loglik_grad(self, theta, want_grad=True, out=None):
+        """theta [B,P] (constrained).  Returns (ll [B], grad [B,P] or None, info [B]) device tensors."""
+        theta = self._dev(theta)
+        if theta.ndim == 1:
+            theta = theta[None, :]
+        B = theta.shape[0]
+        if theta.shape[1] != self.P:
+            raise ValueError(f'theta must have {self.P} columns')
+        ws = self._workspace(B)
+        if out is None:
+            ll = torch.empty(B, dtype=torch.float64, device=self.device)
+            grad = torch.empty(B, self.P, dtype=torch.float64, device=self.device) if want_grad else None
+            info = torch.empty(B, dtype=torch.int32, device=self.device)
+        else:
+            ll, grad, info = out
+        rc = self.lib.avn_gp_loglik_grad(self._h, _ptr(theta), B, _ptr(ll), _ptr(grad), _ptr(info), _ptr(ws),
+                                         ws.numel(), _stream())
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        self._last_B = B
+        return ll, grad, info
+
+    def cov(self, theta):
+        theta = self._dev(theta)
+        if theta.ndim == 1:
+            theta = theta[None, :]
+        B = theta.shape[0]
+        ws = self._workspace(B)
+        K = torch.empty(B, self.npad, self.npad, dtype=torch.float64, device=self.device)
+        rc = self.lib.avn_gp_cov(self._h, _ptr(theta), B, _ptr(K), _ptr(ws), ws.numel(), _stream())
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        return K
+
+    def debug_buffers(self, B=None):
+        """views of the named workspace buffers of the last loglik_grad call (tests / profiling)."""
+        B = B or self._last_B
+        L = _lib.WsLayout()
+        rc = self.lib.avn_gp_workspace_layout(self._h, B, C.byref(L))
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        npad, nb, d, nk = L.npad, L.nb, self.nx, len(self.kerns)
+
+        def view(off, shape):
+            n = int(np.prod(shape))
+            return self._ws[off:off + n * 8].view(torch.float64).view(*shape)
+        out = dict(npad=npad, nb=nb,
+                   xw=view(L.xw, (B, npad, d)), xs=view(L.xs, (B, nk, npad, d)), x2=view(L.x2, (B, nk, npad)),
+                   z=view(L.z, (B, npad)), wstat=view(L.wstat, (B, 16)), kl=view(L.kl, (B, npad, npad)),
+                   t=view(L.t, (B, npad, npad)), beta=view(L.beta, (B, npad)), alpha=view(L.alpha, (B, npad)))
+        if self.n_iw:
+            out['dxw'] = view(L.dxw, (B, npad, d, 8))
+            out['gxpart'] = view(L.gxpart, (B, nb, npad, d))
+        if self.n_cw:
+            out['dz'] = view(L.dz, (B, npad, 8))
+        return out
+
+    # -- predict -----------------------------------------------------------------------------
+    def factorize(self, theta):
+        theta = self._dev(theta).reshape(-1)
+        if theta.shape[0] != self.P:
+            raise ValueError(f'theta must have {self.P} entries')
+        ws = self._workspace(1)
+        sb = self.lib.avn_gp_state_bytes(self._h)
+        if self._state is None or self._state.numel() < sb:
+            self._state = torch.empty(sb, dtype=torch.uint8, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        rc = self.lib.avn_gp_factorize(self._h, _ptr(theta), _ptr(self._state), self._state.numel(), _ptr(info),
+                                       _ptr(ws), ws.numel(), _stream())
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        self._theta_fact = theta
+        return info
+
+    @staticmethod
+    def make_epilogue(mode='latent', deg=8, normvar=False, EIopt=None, yopt=0.0, yrev=None):
+        e = _lib.Epilogue()
+        e.mode = {'latent': 0, 'revert': 1, 'EI': 2}[mode]
+        e.deg = deg
+        e.normvar = 1 if normvar else 0
+        e.ei_max = 1 if EIopt == 'max' else 0
+        e.yopt = float(yopt)
+        if e.mode != 0:
+            if deg < 1 or deg > _lib.AVN_MAX_GH:
+                raise ValueError(f'deg must be in [1,{_lib.AVN_MAX_GH}]')
+            xi, wi = np.polynomial.hermite.hermgauss(deg)
+            for i in range(deg):
+                e.nodes[i] = xi[i]
+                e.weights[i] = wi[i]
+        if yrev:
+            e.yrev = _lib.make_prog(yrev, nparams=0)
+        return e
+
+    def predict(self, Xs, epilogue=None, mean_add=None, max_ws_bytes=4 << 30):
+        """Xs [M,nx] converted test points -> (mean [M], var [M]) device tensors."""
+        if self._state is None:
+            raise GPError('factorize first')
+        Xs = self._dev(Xs)
+        M = Xs.shape[0]
+        if Xs.ndim != 2 or Xs.shape[1] != self.nx:
+            raise ValueError('Xs must be [M,nx]')
+        epi = epilogue if epilogue is not None else self.make_epilogue()
+        need = min(self.lib.avn_gp_predict_workspace_bytes(self._h, M), max_ws_bytes)
+        need = max(need, self.npad * 64 * 8)
+        if self._pws is None or self._pws.numel() < need:
+            self._pws = None
+            self._pws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        mean = torch.empty(M, dtype=torch.float64, device=self.device)
+        var = torch.empty(M, dtype=torch.float64, device=self.device)
+        madd = self._dev(mean_add).reshape(-1) if mean_add is not None else None
+        rc = self.lib.avn_gp_predict(self._h, _ptr(self._state), _ptr(Xs), M, C.byref(epi), _ptr(madd), _ptr(mean),
+                                     _ptr(var), _ptr(self._pws), self._pws.numel(), _stream())
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        return mean, var

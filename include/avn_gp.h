@@ -1,0 +1,139 @@
+/*
+ * avn_gp.h -- C ABI of the B200-native Gaussian-process inner loop of andvaranaut.
+ *
+ * The reference (andrew-angus/andvaranaut) has no FFI of its own: its seam is the Python class
+ * GPMCMC (andvaranaut/gpmcmc.py:30) and, inside it, three third-party call families that this
+ * library replaces one for one:
+ *   (i)   the compiled logp(theta) / dlogp(theta) that pm.find_MAP and pm.sample evaluate
+ *         (gpmcmc.py:310-323 builds them, :332,:345,:351,:357 consume them)      -> avn_gp_loglik_grad
+ *   (ii)  gp.predict(Xnew, point=hypers, diag=True, jitter, pred_noise=True)
+ *         (gpmcmc.py:588-598)                                                    -> avn_gp_factorize + avn_gp_predict
+ *   (iii) the Gauss-Hermite reversion / expected-improvement loop __gh_stats
+ *         (gpmcmc.py:545-569)                                                    -> epilogue of avn_gp_predict
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types; every *_dev pointer is DEVICE memory owned
+ *     by the caller; the library allocates nothing on the device and never frees caller memory.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*) and is asynchronous;
+ *     only avn_gp_create/avn_gp_destroy touch no stream.
+ *   - return value: 0 = ok, negative = bad argument / launch failure (text via avn_last_error()).
+ *     Numerical failure is DATA, not an error: info[b] = k > 0 means pivot k of sample b was not
+ *     positive; then ll[b] = -inf and grad[b,:] = 0 (PyMC's NaN-Cholesky -> -inf convention).
+ *   - all arithmetic is FP64.
+ *
+ * Hyperparameter vector theta (constrained space, one row per sample), in this order
+ * (names as in GPMCMC.hypers, gpmcmc.py:193-208,217-220,255-264,288):
+ *     [gv (only if noise)] [l: d*nkern, kernel-major] [kv: nkern] [iwgp: n_iw] [cw: n_cw, wgp order] [alpha (only if RatQuad)]
+ */
+#ifndef AVN_GP_H
+#define AVN_GP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVN_MAX_D 16        /* input dimensions */
+#define AVN_MAX_KERN 4      /* kernels in one sum/product fold */
+#define AVN_MAX_STAGES 6    /* stages in one composite warp (wgp) */
+#define AVN_MAX_WPARAMS 8   /* learnable parameters of one composite warp */
+#define AVN_MAX_GH 32       /* Gauss-Hermite nodes */
+#define AVN_TILE 64         /* matrices are padded to a multiple of this */
+
+typedef struct avn_gp avn_gp;
+
+/* pm.gp.cov.* used at gpmcmc.py:283-299 */
+enum avn_kernel { AVN_RBF = 0, AVN_MATERN52 = 1, AVN_MATERN32 = 2, AVN_EXPONENTIAL = 3, AVN_RATQUAD = 4 };
+/* '+' / '*' of the kernel string, gpmcmc.py:301-307 */
+enum avn_kop { AVN_ADD = 0, AVN_MUL = 1 };
+/* stages of andvaranaut/transform.py:431-534 */
+enum avn_warp_op {
+  AVN_W_AFFINE_CONST = 0, AVN_W_AFFINE = 1, AVN_W_LOG = 2, AVN_W_ARCSINH = 3, AVN_W_BOXCOX = 4,
+  AVN_W_SINHARCSINH = 5, AVN_W_SAL = 6, AVN_W_KUMARASWAMY = 7, AVN_W_STDSHIFT = 8, AVN_W_MEANSTD = 9,
+  AVN_W_MINSHIFT = 10, AVN_W_STDDEV = 11, AVN_W_MAXMIN = 12, AVN_W_PZERO = 13, AVN_W_BOXCOX_CONST = 14
+};
+
+typedef struct {
+  int32_t op;      /* avn_warp_op */
+  int32_t pidx;    /* index of the stage's first learnable parameter inside its warp's parameter slice, or -1: use c[] */
+  double c[4];     /* constants (frozen coefficients) */
+} avn_warp_stage;
+
+typedef struct {
+  int32_t nstages;  /* 0 = identity (column already converted on the host) */
+  int32_t nparams;  /* learnable parameters consumed by this warp */
+  avn_warp_stage st[AVN_MAX_STAGES];
+} avn_warp_prog;
+
+typedef struct {
+  int32_t d;                       /* nx */
+  int32_t nkern;
+  int32_t kern[AVN_MAX_KERN];      /* avn_kernel */
+  int32_t op[AVN_MAX_KERN];        /* op[m-1] joins kernel m to the running fold */
+  int32_t noise;                   /* 1: theta starts with gv */
+  double jitter;
+  avn_warp_prog xwarp[AVN_MAX_D];  /* learnable input warps (iwgp=True), consumed in dimension order */
+  avn_warp_prog ywarp;             /* learnable output warp (cwgp=True) */
+} avn_model_desc;
+
+/* byte offsets of the named buffers inside a loglik workspace (for tests and profiling) */
+typedef struct {
+  int64_t npad, nb;
+  int64_t xw, dxw, xs, x2, z, dz, wstat, kl, t, beta, alpha, gpart, gxpart, total;
+} avn_ws_layout;
+
+/* Gauss-Hermite reversion / expected improvement, gpmcmc.py:545-569 */
+typedef struct {
+  int32_t mode;        /* 0: return latent mu/var; 1: GH-revert mean/var; 2: EI */
+  int32_t deg;
+  int32_t normvar;
+  int32_t ei_max;      /* EIopt == 'max' */
+  double yopt;
+  double nodes[AVN_MAX_GH];
+  double weights[AVN_MAX_GH];
+  avn_warp_prog yrev;  /* frozen output transform; applied right-to-left */
+} avn_epilogue;
+
+const char* avn_last_error(void);
+int avn_version(void);
+
+int avn_gp_create(const avn_model_desc* desc, avn_gp** out);
+void avn_gp_destroy(avn_gp* gp);
+int avn_gp_num_params(const avn_gp* gp);
+
+/* training data: X [N,d] row-major (columns with a learnable warp RAW, the others already converted),
+ * y [N] (raw, mean-subtracted when the output warp is learnable, else already converted). */
+int avn_gp_set_data(avn_gp* gp, const double* X_dev, const double* y_dev, int64_t N);
+
+size_t avn_gp_workspace_bytes(const avn_gp* gp, int64_t B);
+int avn_gp_workspace_layout(const avn_gp* gp, int64_t B, avn_ws_layout* out);
+
+/* logp / dlogp of the marginal likelihood for B hyperparameter samples at once.
+ * theta [B,P]; ll [B]; grad [B,P] (may be NULL: value only); info [B]. */
+int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B, double* ll_dev, double* grad_dev,
+                       int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* covariance build alone (K + (gv+jitter) I, lower block-triangle valid), K [B,npad,npad] */
+int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
+               void* stream);
+
+/* predict: factorise once for one theta, then stream test points */
+size_t avn_gp_state_bytes(const avn_gp* gp);
+int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state_dev, size_t state_bytes, int32_t* info_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
+size_t avn_gp_predict_workspace_bytes(const avn_gp* gp, int64_t M);
+/* Xs [M,d] converted test points; mean_add [M] or NULL (user mean function evaluated on the host);
+ * out_mean/out_var [M]. */
+int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* Xs_dev, int64_t M, const avn_epilogue* epi,
+                   const double* mean_add_dev, double* out_mean_dev, double* out_var_dev, void* ws_dev,
+                   size_t ws_bytes, void* stream);
+
+/* introspection used by bench.py: number of kernel launches issued by the last call on this handle */
+int64_t avn_gp_last_launch_count(const avn_gp* gp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVN_GP_H */

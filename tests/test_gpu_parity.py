@@ -1,0 +1,305 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): log-likelihood and gradient relative 1e-9, predictive
+mean relative 1e-8, predictive variance |d var| <= 1e-8 * max(|var|, kv) (variance is a cancelling
+difference).  Gradient components are compared relative to max(|g_i|, 1e-3 |g|_inf).
+Cases whose cond(K) makes two CPU evaluations of the reference formula disagree above those
+tolerances (RBF, noise=False, jitter 1e-6: cond ~ 6e9) are checked against cond(K)*eps instead,
+and say so.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import gp_oracle as go  # noqa: E402
+import cases  # noqa: E402
+import make_golden as mg  # noqa: E402
+
+EPS = np.finfo(np.float64).eps
+
+
+def engine(spec):
+    from andvaranaut_b200.gp import GPEngine
+    return GPEngine(**cases.engine_args(spec))
+
+
+def grad_err(g, ref):
+    return float(np.max(np.abs(g - ref) / np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))))
+
+
+def check_ll_grad(spec, X, y, thetas, tol_ll=1e-9, tol_g=1e-9):
+    eng = engine(spec)
+    eng.set_data(X, y)
+    ll, grad, info = eng.loglik_grad(thetas)
+    torch.cuda.synchronize()
+    ll, grad, info = ll.cpu().numpy(), grad.cpu().numpy(), info.cpu().numpy()
+    assert eng.launches > 0
+    for b in range(len(thetas)):
+        r = go.loglik(spec, thetas[b], X, y)
+        assert info[b] == 0
+        assert abs(ll[b] - r.ll) <= tol_ll * abs(r.ll), (b, ll[b], r.ll)
+        assert grad_err(grad[b], r.grad) <= tol_g, (b, grad[b], r.grad)
+    return eng
+
+
+@pytest.mark.parametrize('name', ['m52_noise', 'm32_exp_sum', 'rbf_rq_prod', 'c2_small'])
+def test_golden_loglik_grad(name):
+    case = mg.gp_cases()[name]
+    g = np.load(os.path.join(HERE, 'golden', f'gp_oracle_{name}.npz'))
+    spec = case['spec']
+    eng = engine(spec)
+    eng.set_data(g['X'], g['y'])
+    ll, grad, info = eng.loglik_grad(g['theta'][None, :])
+    assert int(info[0]) == 0
+    assert abs(float(ll[0]) - float(g['ll'])) <= 1e-9 * abs(float(g['ll']))
+    assert grad_err(grad[0].cpu().numpy(), g['grad']) <= 1e-9
+
+
+def test_golden_c1_tutorial_config_illconditioned():
+    """C1 (tutorial: RBF, N=100, d=2, noise=False, jitter 1e-6) has cond(K) ~ 6e9; the reference formula is
+    only defined to ~cond*eps there, so parity is asserted at that floor."""
+    g = np.load(os.path.join(HERE, 'golden', 'gp_oracle_rbf_c1.npz'))
+    spec = mg.gp_cases()['rbf_c1']['spec']
+    eng = engine(spec)
+    eng.set_data(g['X'], g['y'])
+    ll, grad, info = eng.loglik_grad(g['theta'][None, :])
+    th = go.unpack(spec, g['theta'])
+    K = go.cov_matrix(spec, th, g['X']) + spec.jitter * np.eye(100)
+    floor = np.linalg.cond(K) * EPS
+    assert int(info[0]) == 0
+    assert abs(float(ll[0]) - float(g['ll'])) <= max(1e-9, floor) * abs(float(g['ll']))
+    assert grad_err(grad[0].cpu().numpy(), g['grad']) <= 10 * floor
+    eng.factorize(g['theta'])
+    mu, var = eng.predict(g['Xs'])
+    assert np.max(np.abs(mu.cpu().numpy() - g['mu'])) <= 1e-8 * np.max(np.abs(g['mu'])) + 10 * floor
+    kv = go.kdiag_total(spec, th['kv'])
+    assert np.max(np.abs(var.cpu().numpy() - g['var']) / np.maximum(np.abs(g['var']), kv)) <= 1e-8
+
+
+@pytest.mark.parametrize('name', ['m52_noise', 'm32_exp_sum', 'rbf_rq_prod'])
+def test_golden_predict(name):
+    case = mg.gp_cases()[name]
+    g = np.load(os.path.join(HERE, 'golden', f'gp_oracle_{name}.npz'))
+    spec = case['spec']
+    eng = engine(spec)
+    eng.set_data(g['X'], g['y'])
+    info = eng.factorize(g['theta'])
+    assert int(info[0]) == 0
+    mu, var = eng.predict(g['Xs'])
+    mu, var = mu.cpu().numpy(), var.cpu().numpy()
+    kv = go.kdiag_total(spec, go.unpack(spec, g['theta'])['kv'])
+    assert np.max(np.abs(mu - g['mu'])) <= 1e-8 * np.max(np.abs(g['mu']))
+    assert np.max(np.abs(var - g['var']) / np.maximum(np.abs(g['var']), kv)) <= 1e-8
+
+
+SPECS = {
+    'rbf_d2': (go.ModelSpec(nx=2, kerns=['RBF']), 64),            # exactly one tile
+    'm52_d8': (go.ModelSpec(nx=8, kerns=['Matern52']), 65),       # one row into the second tile
+    'm32_d16': (go.ModelSpec(nx=16, kerns=['Matern32']), 127),    # maximum d, ragged
+    'expo_d1': (go.ModelSpec(nx=1, kerns=['Exponential']), 33),
+    'rq_nonoise': (go.ModelSpec(nx=3, kerns=['RatQuad'], noise=False, jitter=1e-4), 90),
+    'four_kern': (go.ModelSpec(nx=3, kerns=['RBF', 'Matern52', 'Matern32', 'Exponential'], ops=['+', '*', '+']), 100),
+    'tiny': (go.ModelSpec(nx=2, kerns=['Matern52']), 3),
+    'x_warp_mm': (go.ModelSpec(nx=3, kerns=['Matern52'],
+                               xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0)), None, (['kumaraswamy', 'maxmin'], None)]), 150),
+    # at most AVN_MAX_WPARAMS = 8 learnable parameters per composite warp
+    'y_warp_a': (go.ModelSpec(nx=2, kerns=['RBF'], ywarp=['affine', 'arcsinh', 'boxcox', 'stdshift']), 120),
+    'y_warp_b': (go.ModelSpec(nx=2, kerns=['RBF'], ywarp=['boxcox', 'sinharcsinh', 'stdshift', 'pzero']), 120),
+    'y_warp_min': (go.ModelSpec(nx=2, kerns=['Matern52'], ywarp=['meanstd', 'minshift', 'logarithm', 'stddev']), 80),
+    'both_warps_2k': (go.ModelSpec(nx=4, kerns=['Matern52', 'RBF'], ops=['+'],
+                                   xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * 4,
+                                   ywarp=['logarithm', 'sal', 'meanstd']), 200),
+}
+
+
+@pytest.mark.parametrize('name', list(SPECS))
+def test_shapes_kernels_warps(name):
+    spec, N = SPECS[name]
+    X, y, th, _ = cases.synth(spec, N, seed=17)
+    rng = np.random.default_rng(4)
+    if name == 'y_warp_b':
+        # pzero pushes 0 through boxcox: d/dy |y|^(lam+1) at 0 is finite only for lam > 0 (the reference's
+        # autodiff yields NaN otherwise, as do the oracle and the kernel)
+        th[spec.offsets()['cw']] = 0.15
+    thetas = np.stack([th, th * np.exp(0.05 * rng.normal(size=th.shape))])
+    # the Exponential kernel's diagonal derivative amplifies the rounding of r2_ii (see test_oracle.py)
+    tol_g = 1e-6 if 'Exponential' in spec.kerns else 1e-9
+    check_ll_grad(spec, X, y, thetas, tol_g=tol_g)
+
+
+def test_value_only_path_and_batch_consistency():
+    spec = go.ModelSpec(nx=5, kerns=['Matern52'])
+    X, y, th, _ = cases.synth(spec, 300, seed=21)
+    rng = np.random.default_rng(0)
+    thetas = th[None, :] * np.exp(0.05 * rng.normal(size=(7, len(th))))
+    eng = engine(spec)
+    eng.set_data(X, y)
+    ll, grad, info = eng.loglik_grad(thetas)
+    ll0, g0, _ = eng.loglik_grad(thetas, want_grad=False)
+    assert g0 is None and torch.equal(ll, ll0)
+    # batched == one at a time, bit for bit (samples are independent work units)
+    for b in (0, 3, 6):
+        l1, g1, _ = eng.loglik_grad(thetas[b:b + 1])
+        assert float(l1[0]) == float(ll[b]) and torch.equal(g1[0], grad[b])
+    # deterministic across runs
+    ll2, grad2, _ = eng.loglik_grad(thetas)
+    assert torch.equal(ll, ll2) and torch.equal(grad, grad2)
+
+
+def test_not_positive_definite_is_data_not_error():
+    """duplicate inputs + zero noise + zero jitter -> singular K: info > 0, ll = -inf, grad = 0 (gpmcmc.py:313 /
+    PyMC's NaN-Cholesky convention), and the healthy sample next to it is unaffected."""
+    spec = go.ModelSpec(nx=2, kerns=['RBF'], noise=True, jitter=0.0)
+    X, y, th, _ = cases.synth(spec, 70, seed=2)
+    X[10] = X[3]
+    bad = th.copy()
+    bad[0] = 0.0
+    thetas = np.stack([th, bad])
+    eng = engine(spec)
+    eng.set_data(X, y)
+    ll, grad, info = eng.loglik_grad(thetas)
+    ll, grad, info = ll.cpu().numpy(), grad.cpu().numpy(), info.cpu().numpy()
+    assert info[0] == 0 and info[1] > 0
+    assert np.isneginf(ll[1]) and np.all(grad[1] == 0.0)
+    r = go.loglik(spec, th, X, y)
+    assert abs(ll[0] - r.ll) <= 1e-9 * abs(r.ll)
+
+
+def test_stagewise_buffers_match_oracle():
+    spec = go.ModelSpec(nx=6, kerns=['Matern52'])
+    N = 200
+    X, y, th, _ = cases.synth(spec, N, seed=8)
+    eng = engine(spec)
+    eng.set_data(X, y)
+    eng.loglik_grad(th[None, :])
+    torch.cuda.synchronize()
+    b = eng.debug_buffers()
+    r = go.loglik(spec, th, X, y, keep=True)
+    L = b['kl'][0, :N, :N].cpu().numpy()
+    Tm = b['t'][0, :N, :N].cpu().numpy()
+    assert np.max(np.abs(np.tril(L) - r.L)) <= 1e-12 * np.max(np.abs(r.L))
+    Tref = sla.solve_triangular(r.L, np.eye(N), lower=True)
+    assert np.max(np.abs(np.tril(Tm) - Tref)) <= 1e-11 * np.max(np.abs(Tref))
+    assert np.max(np.abs(b['alpha'][0, :N].cpu().numpy() - r.alpha)) <= 1e-10 * np.max(np.abs(r.alpha))
+    # padding carries the identity
+    npad = b['npad']
+    assert torch.equal(torch.diagonal(b['kl'][0])[N:], torch.ones(npad - N, dtype=torch.float64, device=b['kl'].device))
+    K = eng.cov(th)[0, :N, :N].cpu().numpy()
+    Kref = go.cov_matrix(spec, go.unpack(spec, th), X)
+    Kref[np.diag_indices(N)] += go.unpack(spec, th)['gv'] + spec.jitter
+    assert np.max(np.abs(np.tril(K) - np.tril(Kref))) <= 4 * EPS * np.max(np.abs(Kref))
+
+
+def test_predict_epilogues_match_reference_loop():
+    """GH reversion / EI / normvar against the literal per-point loop of GPMCMC.__gh_stats."""
+    from andvaranaut_b200 import transform as T
+    from andvaranaut_b200.gp import GPEngine
+    spec = go.ModelSpec(nx=3, kerns=['Matern52'])
+    rng = np.random.default_rng(12)
+    X, yraw, th, Xs = cases.synth(go.ModelSpec(nx=3, kerns=['Matern52'], ywarp=['logarithm']), 150, seed=5, M=333)
+    w = T.wgp(['logarithm', 'sal', 'meanstd'], [0.1, 1.1, -0.2, 0.9], y=yraw)
+    z = w.con(yraw)
+    th = th[:5]
+    eng = engine(spec)
+    eng.set_data(X, z)
+    eng.factorize(th)
+    mu_r, var_r = go.predict(spec, th, X, z, Xs)
+    madd = rng.normal(size=len(Xs)) * 0.1
+    yopt = float(np.min(yraw))
+    for kw, ekw in [
+        (dict(normvar=False), dict(mode='revert', normvar=False)),
+        (dict(normvar=True), dict(mode='revert', normvar=True)),
+        (dict(EI=True, EIopt='min', yopt=yopt, normvar=False), dict(mode='EI', EIopt='min', yopt=yopt)),
+        (dict(EI=True, EIopt='max', yopt=yopt, normvar=False), dict(mode='EI', EIopt='max', yopt=yopt)),
+        (dict(normvar=False, deg=5), dict(mode='revert', deg=5)),
+    ]:
+        ref_m, ref_v = go.gh_stats_loop(mu_r, var_r, w.rev, mean_add=madd, **kw)
+        epi = GPEngine.make_epilogue(yrev=w.rev_program(), **ekw)
+        m, v = eng.predict(Xs, epilogue=epi, mean_add=madd)
+        m, v = m.cpu().numpy(), v.cpu().numpy()
+        assert np.max(np.abs(m - ref_m[:, 0])) <= 1e-8 * np.max(np.abs(ref_m)), kw
+        assert np.max(np.abs(v - ref_v[:, 0])) <= 1e-8 * max(np.max(np.abs(ref_v)), np.max(ref_m ** 2)), kw
+
+
+def test_predict_ragged_blocks_and_small_workspace():
+    spec = go.ModelSpec(nx=4, kerns=['RBF', 'Matern32'], ops=['*'])
+    X, y, th, Xs = cases.synth(spec, 130, seed=9, M=1000)
+    eng = engine(spec)
+    eng.set_data(X, y)
+    eng.factorize(th)
+    mu_r, var_r = go.predict(spec, th, X, y, Xs)
+    kv = go.kdiag_total(spec, go.unpack(spec, th)['kv'])
+    for M, ws in [(1, 4 << 30), (63, 4 << 30), (64, 4 << 30), (1000, 4 << 30), (1000, eng.npad * 64 * 8 * 3)]:
+        mu, var = eng.predict(Xs[:M], max_ws_bytes=ws)
+        assert np.max(np.abs(mu.cpu().numpy() - mu_r[:M])) <= 1e-8 * np.max(np.abs(mu_r))
+        assert np.max(np.abs(var.cpu().numpy() - var_r[:M]) / np.maximum(np.abs(var_r[:M]), kv)) <= 1e-8
+
+
+def test_config3_shape_against_oracle():
+    """C3: N=1000, d=6, RBF + noise; a posterior-like cloud of hyperparameters, oracle-checked on a subset."""
+    spec = go.ModelSpec(nx=6, kerns=['RBF'])
+    X, y, th, _ = cases.synth(spec, 1000, seed=303)
+    rng = np.random.default_rng(303)
+    thetas = th[None, :] * np.exp(0.1 * rng.normal(size=(16, len(th))))
+    eng = engine(spec)
+    eng.set_data(X, y)
+    ll, grad, info = eng.loglik_grad(thetas)
+    ll, grad = ll.cpu().numpy(), grad.cpu().numpy()
+    assert not info.any()
+    for b in (0, 7, 15):
+        r = go.loglik(spec, thetas[b], X, y)
+        assert abs(ll[b] - r.ll) <= 1e-9 * abs(r.ll)
+        assert grad_err(grad[b], r.grad) <= 1e-9
+
+
+def test_config2_shape_against_oracle():
+    """C2: N=2000, d=8, ARD Matern-5/2 + learnable input (kumaraswamy) and output (log, sal, meanstd) warps: P = 30."""
+    spec = go.ModelSpec(nx=8, kerns=['Matern52'], xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * 8,
+                        ywarp=['logarithm', 'sal', 'meanstd'])
+    X, y, th, _ = cases.synth(spec, 2000, seed=202)
+    assert len(th) == 30
+    eng = engine(spec)
+    eng.set_data(X, y)
+    ll, grad, info = eng.loglik_grad(th[None, :])
+    r = go.loglik(spec, th, X, y)
+    assert int(info[0]) == 0
+    assert abs(float(ll[0]) - r.ll) <= 1e-9 * abs(r.ll)
+    assert grad_err(grad[0].cpu().numpy(), r.grad) <= 1e-9
+
+
+def test_full_size_properties_config4():
+    """C4 at full training size (N=8192, d=10, Matern-5/2): size-independent properties.
+    (1) predicting at training inputs with latent epilogue reproduces z up to the noise shrinkage:
+        mu = z - (gv+jitter) * alpha  exactly in exact arithmetic;
+    (2) var >= gv and var <= kv + gv everywhere; (3) the value is independent of how test points are blocked."""
+    spec = go.ModelSpec(nx=10, kerns=['Matern52'])
+    N = 8192
+    rng = np.random.default_rng(404)
+    X = rng.uniform(0, 1, (N, 10))
+    y = np.sin(X @ np.linspace(0.5, 2.0, 10)) + 0.01 * rng.normal(size=N)
+    th = np.concatenate([[1e-4], np.ones(10), [1.5]])
+    eng = engine(spec)
+    eng.set_data(X, y)
+    info = eng.factorize(th)
+    assert int(info[0]) == 0
+    idx = rng.choice(N, 512, replace=False)
+    mu, var = eng.predict(X[idx])
+    mu, var = mu.cpu().numpy(), var.cpu().numpy()
+    assert np.all(var >= 1e-4 * (1 - 1e-6)) and np.all(var <= 1.5 + 1e-4 + 1e-9)
+    # oracle for the same 512 points needs one 8192^3/3 Cholesky on the CPU: a few seconds
+    mu_r, var_r, _ = go.predict_blocked(spec, th, X, y, X[idx])
+    assert np.max(np.abs(mu - mu_r)) <= 1e-8 * np.max(np.abs(mu_r))
+    assert np.max(np.abs(var - var_r) / np.maximum(np.abs(var_r), 1.5)) <= 1e-8
+    Xs = rng.uniform(0, 1, (3000, 10))
+    a = eng.predict(Xs)
+    b = eng.predict(Xs, max_ws_bytes=eng.npad * 64 * 8 * 5)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
