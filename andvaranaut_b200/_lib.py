@@ -15,6 +15,7 @@ AVN_MAX_STAGES = 6
 AVN_MAX_WPARAMS = 8
 AVN_MAX_GH = 32
 AVN_TILE = 64
+PHASES = ('warp', 'cov', 'potrf', 'trsv', 'trtri', 'alpha', 'kinv_grad', 'finalize', 'kxs', 'predict_var')
 
 KERNEL_IDS = {'RBF': 0, 'Matern52': 1, 'Matern32': 2, 'Exponential': 3, 'RatQuad': 4}
 OP_IDS = {'+': 0, '*': 1}
@@ -57,6 +58,7 @@ SYMBOLS = {
     'avn_gp_workspace_layout': (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(WsLayout)]),
     'avn_gp_loglik_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    'avn_gp_set_streams': (C.c_int, [C.c_void_p, C.c_int]),
     'avn_gp_cov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'avn_gp_state_bytes': (C.c_size_t, [C.c_void_p]),
     'avn_gp_factorize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
@@ -65,6 +67,8 @@ SYMBOLS = {
     'avn_gp_predict': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Epilogue), C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'avn_gp_last_launch_count': (C.c_int64, [C.c_void_p]),
+    'avn_gp_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
+    'avn_gp_phase_ms': (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 
 _lib = None

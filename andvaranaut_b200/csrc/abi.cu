@@ -27,7 +27,33 @@ struct avn_gp {
   int64_t N = 0;
   int64_t launches = 0;
   bool has_xwarp = false;
+  bool profiling = false;
+  int max_groups = 4;                 // independent sample groups run on internal streams
+  cudaStream_t gstream[8] = {};
+  cudaEvent_t gev[9] = {};            // [0]: fork point on the caller's stream, [1+g]: join of group g
+  cudaEvent_t ev[2 * AVN_PH_COUNT] = {};
+  bool ev_used[AVN_PH_COUNT] = {};
+  double acc_ms[AVN_PH_COUNT] = {};
 };
+
+// RAII phase marker: records start/stop events when profiling is on
+struct Phase {
+  avn_gp* gp;
+  int id;
+  cudaStream_t st;
+  Phase(avn_gp* g, int i, cudaStream_t s) : gp(g), id(i), st(s) {
+    if (gp->profiling) cudaEventRecord(gp->ev[2 * id], st);
+  }
+  ~Phase() {
+    if (gp->profiling) {
+      cudaEventRecord(gp->ev[2 * id + 1], st);
+      gp->ev_used[id] = true;
+    }
+  }
+};
+static void phases_reset(avn_gp* gp) {
+  for (int i = 0; i < AVN_PH_COUNT; i++) gp->ev_used[i] = false;
+}
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t npad_of(int64_t N) { return align_up(N < 1 ? 1 : N, TILE); }
@@ -99,7 +125,44 @@ extern "C" int avn_gp_create(const avn_model_desc* desc, avn_gp** out) {
   return 0;
 }
 
-extern "C" void avn_gp_destroy(avn_gp* gp) { delete gp; }
+extern "C" void avn_gp_destroy(avn_gp* gp) {
+  if (!gp) return;
+  for (auto& e : gp->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : gp->gev)
+    if (e) cudaEventDestroy(e);
+  for (auto& s : gp->gstream)
+    if (s) cudaStreamDestroy(s);
+  delete gp;
+}
+
+extern "C" int avn_gp_set_profiling(avn_gp* gp, int enable) {
+  if (!gp) return fail("avn_gp_set_profiling: null handle");
+  if (enable && !gp->ev[0]) {
+    for (auto& e : gp->ev) {
+      cudaError_t err = cudaEventCreate(&e);
+      if (err != cudaSuccess) return fail_cuda("cudaEventCreate", err);
+    }
+  }
+  gp->profiling = enable != 0;
+  return 0;
+}
+
+extern "C" int avn_gp_phase_ms(avn_gp* gp, double* out_ms) {
+  if (!gp || !out_ms) return fail("avn_gp_phase_ms: null argument");
+  for (int i = 0; i < AVN_PH_COUNT; i++) {
+    out_ms[i] = 0.0;
+    if (gp->profiling && gp->ev_used[i]) {
+      cudaError_t err = cudaEventSynchronize(gp->ev[2 * i + 1]);
+      if (err != cudaSuccess) return fail_cuda("cudaEventSynchronize", err);
+      float ms = 0.f;
+      err = cudaEventElapsedTime(&ms, gp->ev[2 * i], gp->ev[2 * i + 1]);
+      if (err != cudaSuccess) return fail_cuda("cudaEventElapsedTime", err);
+      out_ms[i] = ms;
+    }
+  }
+  return 0;
+}
 extern "C" int avn_gp_num_params(const avn_gp* gp) { return gp ? gp->kd.P : -1; }
 extern "C" int64_t avn_gp_last_launch_count(const avn_gp* gp) { return gp ? gp->launches : -1; }
 
@@ -176,6 +239,7 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
 
 // conversions + scaled inputs for B samples
 static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st) {
+  Phase ph(gp, AVN_PH_WARP, st);
   warp_kernel<<<(unsigned)B, 256, 0, st>>>(gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W);
   LAUNCH_CHECK("warp_kernel");
   return 0;
@@ -183,6 +247,7 @@ static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W,
 
 static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, double* Kout,
                    cudaStream_t st) {
+  Phase ph(gp, AVN_PH_COV, st);
   const KernDesc& kd = gp->kd;
   const int64_t nb = npad / TILE, ntiles = nb * (nb + 1) / 2;
   size_t smem = (size_t)(2 * kd.nkern * TILE * kd.d + 2 * kd.nkern * TILE) * 8;
@@ -195,8 +260,6 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
   return 0;
 }
 
-static const size_t kDiagSmem = (size_t)2 * TILE * (TILE + 1) * 8;
-
 // Cholesky K -> L in place (kl), diagonal-block inverses into t, then the rest of T = L^-1
 static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* info, int64_t npad, bool want_inverse,
                       cudaStream_t st) {
@@ -208,17 +271,18 @@ static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* inf
     cudaError_t e = opt_in_smem(potrf_update_kernel<BM>, PG::SMEM_BYTES);
     if (e == cudaSuccess) e = opt_in_smem(potrf_panel_kernel<BM>, PG::SMEM_BYTES);
     if (e == cudaSuccess) e = opt_in_smem(trtri_row_kernel, TrtriG::SMEM_BYTES);
-    if (e == cudaSuccess) e = opt_in_smem(potrf_diag_kernel, kDiagSmem);
     if (e != cudaSuccess) return fail_cuda("factor smem opt-in", e);
     attr_done = true;
   }
+  {
+  Phase ph(gp, AVN_PH_POTRF, st);
   for (int k = 0; k < nb; k++) {
     if (k > 0) {
       int rows = (nb - k) * TILE;
       potrf_update_kernel<BM><<<dim3((rows + BM - 1) / BM, (unsigned)B), PG::NTHREADS, PG::SMEM_BYTES, st>>>(kl, (int)npad, k);
       LAUNCH_CHECK("potrf_update_kernel");
     }
-    potrf_diag_kernel<<<(unsigned)B, 256, kDiagSmem, st>>>(kl, t, (int)npad, k, info);
+    potrf_diag_kernel<<<(unsigned)B, TILE, 0, st>>>(kl, t, (int)npad, k, info);
     LAUNCH_CHECK("potrf_diag_kernel");
     if (k + 1 < nb) {
       int rows = (nb - k - 1) * TILE;
@@ -226,7 +290,9 @@ static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* inf
       LAUNCH_CHECK("potrf_panel_kernel");
     }
   }
+  }
   if (want_inverse) {
+    Phase ph(gp, AVN_PH_TRTRI, st);
     for (int i = 1; i < nb; i++) {
       trtri_row_kernel<<<dim3(i, (unsigned)B), TrtriG::NTHREADS, TrtriG::SMEM_BYTES, st>>>(kl, t, (int)npad, i);
       LAUNCH_CHECK("trtri_row_kernel");
@@ -241,9 +307,13 @@ static int run_trsv_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, 
     cudaError_t e = opt_in_smem(trsv_kernel, smem);
     if (e != cudaSuccess) return fail_cuda("trsv smem", e);
   }
-  trsv_kernel<<<(unsigned)B, 256, smem, st>>>(W.kl, W.t, W.z, (int)npad, W.beta, W.wstat);
-  LAUNCH_CHECK("trsv_kernel");
+  {
+    Phase ph(gp, AVN_PH_TRSV, st);
+    trsv_kernel<<<(unsigned)B, 256, smem, st>>>(W.kl, W.t, W.z, (int)npad, W.beta, W.wstat);
+    LAUNCH_CHECK("trsv_kernel");
+  }
   if (want_alpha) {
+    Phase ph(gp, AVN_PH_ALPHA, st);
     alpha_kernel<<<dim3((unsigned)(npad / TILE), (unsigned)B), 256, 0, st>>>(W.t, W.beta, (int)npad, W.alpha);
     LAUNCH_CHECK("alpha_kernel");
   }
@@ -259,11 +329,79 @@ extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double
   layout(gp, B, &L);
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_cov: workspace too small");
   gp->launches = 0;
+  phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WsPtrs W = ws_ptrs(L, ws_dev);
   int rc = run_warp(gp, theta_dev, B, W, L.npad, st);
   if (rc) return rc;
   return run_cov(gp, theta_dev, B, W, L.npad, K_dev, st);
+}
+
+static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& L, int64_t b0) {
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = L.npad, nb = L.nb, ntiles = nb * (nb + 1) / 2;
+  WsPtrs p = W;
+  p.xw += b0 * npad * kd.d;
+  p.dxw += b0 * npad * kd.d * MAXWP;
+  p.xs += b0 * kd.nkern * npad * kd.d;
+  p.x2 += b0 * kd.nkern * npad;
+  p.z += b0 * npad;
+  p.dz += b0 * npad * MAXWP;
+  p.wstat += b0 * WSTAT;
+  p.kl += b0 * npad * npad;
+  p.t += b0 * npad * npad;
+  p.beta += b0 * npad;
+  p.alpha += b0 * npad;
+  p.gpart += b0 * ntiles * MAXACC;
+  p.gxpart += b0 * nb * npad * kd.d;
+  return p;
+}
+
+// the whole evaluation for samples [b0, b0+Bg) on one stream
+static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll, double* grad, int32_t* info,
+                        const WsPtrs& W, const avn_ws_layout& L, cudaStream_t st) {
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = L.npad, nb = L.nb, ntiles = nb * (nb + 1) / 2;
+  const bool want_grad = grad != nullptr;
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t) * Bg, st);
+  if (e != cudaSuccess) return fail_cuda("memset info", e);
+  int rc = run_warp(gp, theta, Bg, W, npad, st);
+  if (rc) return rc;
+  rc = run_cov(gp, theta, Bg, W, npad, W.kl, st);
+  if (rc) return rc;
+  rc = run_factor(gp, Bg, W.kl, W.t, info, npad, want_grad, st);
+  if (rc) return rc;
+  rc = run_trsv_alpha(gp, Bg, W, npad, want_grad, st);
+  if (rc) return rc;
+  if (want_grad) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      e = opt_in_smem(kinv_grad_kernel<false>, KinvG::SMEM_BYTES);
+      if (e == cudaSuccess) e = opt_in_smem(kinv_grad_kernel<true>, KinvG::SMEM_BYTES);
+      if (e != cudaSuccess) return fail_cuda("kinv_grad smem opt-in", e);
+      attr_done = true;
+    }
+    Phase ph(gp, AVN_PH_KINV_GRAD, st);
+    if (gp->has_xwarp)
+      kinv_grad_kernel<true><<<dim3((unsigned)ntiles, (unsigned)Bg), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
+          kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
+    else
+      kinv_grad_kernel<false><<<dim3((unsigned)ntiles, (unsigned)Bg), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
+          kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
+    LAUNCH_CHECK("kinv_grad_kernel");
+  }
+  Phase phf(gp, AVN_PH_FINALIZE, st);
+  finalize_kernel<<<(unsigned)Bg, 256, 0, st>>>(kd, gp->progs, (int)gp->N, (int)npad, (int)ntiles, want_grad ? 1 : 0,
+                                                theta, W, info, ll, grad);
+  LAUNCH_CHECK("finalize_kernel");
+  return 0;
+}
+
+extern "C" int avn_gp_set_streams(avn_gp* gp, int max_groups) {
+  if (!gp) return fail("avn_gp_set_streams: null handle");
+  if (max_groups < 1 || max_groups > 8) return fail("avn_gp_set_streams: max_groups out of range [1,8]");
+  gp->max_groups = max_groups;
+  return 0;
 }
 
 extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B, double* ll_dev, double* grad_dev,
@@ -275,41 +413,41 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
   layout(gp, B, &L);
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_loglik_grad: workspace too small");
   gp->launches = 0;
+  phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WsPtrs W = ws_ptrs(L, ws_dev);
-  const KernDesc& kd = gp->kd;
-  const int64_t npad = L.npad, nb = L.nb, ntiles = nb * (nb + 1) / 2;
-  const bool want_grad = grad_dev != nullptr;
-  cudaError_t e = cudaMemsetAsync(info_dev, 0, sizeof(int32_t) * B, st);
-  if (e != cudaSuccess) return fail_cuda("memset info", e);
-  int rc = run_warp(gp, theta_dev, B, W, npad, st);
-  if (rc) return rc;
-  rc = run_cov(gp, theta_dev, B, W, npad, W.kl, st);
-  if (rc) return rc;
-  rc = run_factor(gp, B, W.kl, W.t, info_dev, npad, want_grad, st);
-  if (rc) return rc;
-  rc = run_trsv_alpha(gp, B, W, npad, want_grad, st);
-  if (rc) return rc;
-  if (want_grad) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      e = opt_in_smem(kinv_grad_kernel<false>, KinvG::SMEM_BYTES);
-      if (e == cudaSuccess) e = opt_in_smem(kinv_grad_kernel<true>, KinvG::SMEM_BYTES);
-      if (e != cudaSuccess) return fail_cuda("kinv_grad smem opt-in", e);
-      attr_done = true;
+  const int P = gp->kd.P;
+  // Samples are independent: split them into groups that run the whole sequence on internal streams, so the
+  // latency-bound steps of one group (diagonal blocks, short panels, tails) overlap the DMMA-bound steps of
+  // another.  Phase timing needs one ordered stream, so profiling forces a single group.
+  int G = gp->profiling ? 1 : gp->max_groups;
+  if (B < 8 * G) G = (int)(B / 8 > 0 ? B / 8 : 1);
+  if (G <= 1) return loglik_group(gp, theta_dev, B, ll_dev, grad_dev, info_dev, W, L, st);
+  for (int g = 0; g < G; g++)
+    if (!gp->gstream[g]) {
+      cudaError_t e = cudaStreamCreateWithFlags(&gp->gstream[g], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return fail_cuda("cudaStreamCreate", e);
     }
-    if (gp->has_xwarp)
-      kinv_grad_kernel<true><<<dim3((unsigned)ntiles, (unsigned)B), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
-          kd, (int)gp->N, (int)npad, theta_dev, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
-    else
-      kinv_grad_kernel<false><<<dim3((unsigned)ntiles, (unsigned)B), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
-          kd, (int)gp->N, (int)npad, theta_dev, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
-    LAUNCH_CHECK("kinv_grad_kernel");
+  for (int g = 0; g <= G; g++)
+    if (!gp->gev[g]) {
+      cudaError_t e = cudaEventCreateWithFlags(&gp->gev[g], cudaEventDisableTiming);
+      if (e != cudaSuccess) return fail_cuda("cudaEventCreate", e);
+    }
+  cudaError_t e = cudaEventRecord(gp->gev[0], st);
+  if (e != cudaSuccess) return fail_cuda("fork event", e);
+  int rc = 0;
+  for (int g = 0; g < G; g++) {
+    const int64_t b0 = B * g / G, b1 = B * (g + 1) / G;
+    cudaStream_t gs = gp->gstream[g];
+    cudaStreamWaitEvent(gs, gp->gev[0], 0);
+    WsPtrs Wg = ws_offset(W, gp, L, b0);
+    rc = loglik_group(gp, theta_dev + b0 * P, b1 - b0, ll_dev + b0, grad_dev ? grad_dev + b0 * P : nullptr,
+                      info_dev + b0, Wg, L, gs);
+    cudaEventRecord(gp->gev[1 + g], gs);
+    cudaStreamWaitEvent(st, gp->gev[1 + g], 0);  // join even on error so the caller's stream stays ordered
+    if (rc) break;
   }
-  finalize_kernel<<<(unsigned)B, 256, 0, st>>>(kd, gp->progs, (int)gp->N, (int)npad, (int)ntiles, want_grad ? 1 : 0,
-                                               theta_dev, W, info_dev, ll_dev, grad_dev);
-  LAUNCH_CHECK("finalize_kernel");
-  return 0;
+  return rc;
 }
 
 // ---- predict -------------------------------------------------------------------------------------
@@ -362,6 +500,7 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_factorize: workspace too small");
   if (state_bytes < (size_t)S.total) return fail("avn_gp_factorize: state buffer too small");
   gp->launches = 0;
+  phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WsPtrs W = ws_ptrs(L, ws_dev);
   char* sb = static_cast<char*>(state_dev);
@@ -410,6 +549,7 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   const int64_t cols_cap = (int64_t)(ws_bytes / (npad * 8)) / TILE * TILE;
   if (cols_cap < TILE) return fail("avn_gp_predict: workspace too small");
   gp->launches = 0;
+  phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char* sb = static_cast<const char*>(state_dev);
   const HypS* hyp = reinterpret_cast<const HypS*>(sb + S.hyp);
@@ -428,9 +568,13 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
     const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
     const unsigned nblk = (unsigned)(cols / TILE);
-    kxs_kernel<<<nblk, 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols,
-                                            Kxs, out_mean_dev);
-    LAUNCH_CHECK("kxs_kernel");
+    {
+      Phase ph(gp, AVN_PH_KXS, st);
+      kxs_kernel<<<nblk, 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols,
+                                              Kxs, out_mean_dev);
+      LAUNCH_CHECK("kxs_kernel");
+    }
+    Phase ph2(gp, AVN_PH_PREDICT_VAR, st);
     predict_var_kernel<<<nblk, PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0,
                                                                          *epi, mean_add_dev, out_mean_dev, out_var_dev);
     LAUNCH_CHECK("predict_var_kernel");

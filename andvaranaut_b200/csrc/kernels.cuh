@@ -213,69 +213,73 @@ __global__ void __launch_bounds__(PotrfCfg<BM>::G::NTHREADS) potrf_panel_kernel(
     }
 }
 
-// diagonal block: unblocked Cholesky + triangular inverse in shared memory.  grid (B), 256 threads.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lall, double* __restrict__ Tall,
-                                                         int npad, int kblk, int32_t* __restrict__ info) {
-  constexpr int LD = TILE + 1;
-  extern __shared__ double smem[];
-  double* A = smem;
-  double* Ti = smem + TILE * LD;
-  const int b = blockIdx.x, tid = threadIdx.x;
+// diagonal block: unblocked Cholesky + triangular inverse.  grid (B), 64 threads.
+// Thread i keeps row i of the block in registers (fully unrolled, static indexing); each of the 64
+// column steps publishes the scaled column through shared memory (2 barriers of 2 warps) and every
+// thread applies the rank-1 update to its row.  The inverse is computed column-per-thread from the
+// shared copy of L (all lanes read the same L element: broadcast, no conflicts).
+constexpr int DIAG_LD = TILE + 2;
+__global__ void __launch_bounds__(TILE) potrf_diag_kernel(double* __restrict__ Lall, double* __restrict__ Tall,
+                                                          int npad, int kblk, int32_t* __restrict__ info) {
+  __shared__ __align__(16) double Ls[TILE * DIAG_LD];
+  __shared__ __align__(16) double col[TILE];
+  __shared__ double pivinv;
+  const int b = blockIdx.x, i = threadIdx.x;
   double* Lkk = Lall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
   double* Tkk = Tall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
-  for (int e = tid; e < TILE * TILE; e += 256) {
-    int i = e >> 6, c = e & 63;
-    A[i * LD + c] = (c <= i) ? Lkk[(int64_t)i * npad + c] : 0.0;
-  }
+  // coalesced load through shared memory
+  for (int e = i; e < TILE * TILE; e += TILE) Ls[(e >> 6) * DIAG_LD + (e & 63)] = Lkk[(int64_t)(e >> 6) * npad + (e & 63)];
   __syncthreads();
+  double a[TILE];
+#pragma unroll
+  for (int c = 0; c < TILE; c++) a[c] = (c <= i) ? Ls[i * DIAG_LD + c] : 0.0;
+  __syncthreads();
+  double myinv = 1.0;  // 1 / L_ii of this thread's row
+#pragma unroll
   for (int j = 0; j < TILE; j++) {
-    double dj = A[j * LD + j];
-    if (!(dj > 0.0)) {  // also catches NaN
-      if (tid == 0 && info[b] == 0) info[b] = kblk * TILE + j + 1;
-      dj = 1.0;
-    }
-    const double ljj = sqrt(dj);
-    const double inv = 1.0 / ljj;
-    __syncthreads();
-    if (tid < TILE) {
-      if (tid == j) A[j * LD + j] = ljj;
-      else if (tid > j) A[tid * LD + j] *= inv;
-    }
-    __syncthreads();
-    // trailing update of the lower triangle right of column j
-    const int rem = TILE - 1 - j;  // rows/cols j+1 .. 63
-    for (int e = tid; e < rem * rem; e += 256) {
-      int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) A[i * LD + c] -= A[i * LD + j] * A[c * LD + j];
-    }
-    __syncthreads();
-  }
-  // T = L^-1: 4 threads per column c split the dot products
-  {
-    const int c = tid >> 2, part = tid & 3;
-    for (int i = 0; i < TILE; i++) {
-      // all threads walk rows together; x[i] depends on x[c..i-1] written in earlier iterations
-      double s = 0.0;
-      if (i > c)
-        for (int k = c + part; k < i; k += 4) s += A[i * LD + k] * Ti[k * LD + c];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0) {
-        double v;
-        if (i < c) v = 0.0;
-        else if (i == c) v = 1.0 / A[i * LD + i];
-        else v = -s / A[i * LD + i];
-        Ti[i * LD + c] = v;
+    if (i == j) {
+      double dj = a[j];
+      if (!(dj > 0.0)) {  // also catches NaN
+        if (info[b] == 0) info[b] = kblk * TILE + j + 1;
+        dj = 1.0;
       }
-      __syncwarp();
+      const double ljj = sqrt(dj);
+      a[j] = ljj;
+      myinv = 1.0 / ljj;
+      pivinv = myinv;
     }
+    __syncthreads();
+    double lij = 0.0;
+    if (i > j) {
+      lij = a[j] * pivinv;
+      a[j] = lij;
+    }
+    col[i] = lij;
+    __syncthreads();
+#pragma unroll
+    for (int c = j + 1; c < TILE; c++) a[c] = fma(-lij, col[c], a[c]);
   }
+  // rows back to shared memory (upper part zero), reciprocal diagonal in col[]
+#pragma unroll
+  for (int c = 0; c < TILE; c++) Ls[i * DIAG_LD + c] = (c <= i) ? a[c] : 0.0;
+  col[i] = myinv;
   __syncthreads();
-  for (int e = tid; e < TILE * TILE; e += 256) {
-    int i = e >> 6, c = e & 63;
-    Lkk[(int64_t)i * npad + c] = (c <= i) ? A[i * LD + c] : 0.0;
-    Tkk[(int64_t)i * npad + c] = Ti[i * LD + c];
+  // T = L^-1, thread c owns column c:  x_r = (delta_rc - sum_{k<r} L_rk x_k) / L_rr
+  double x[TILE];
+#pragma unroll
+  for (int r = 0; r < TILE; r++) {
+    double s = (r == i) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < r; k++) s = fma(-Ls[r * DIAG_LD + k], x[k], s);
+    x[r] = s * col[r];
   }
+  // write L (coalesced from shared) and T (through shared, then coalesced)
+  for (int e = i; e < TILE * TILE; e += TILE) Lkk[(int64_t)(e >> 6) * npad + (e & 63)] = Ls[(e >> 6) * DIAG_LD + (e & 63)];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < TILE; r++) Ls[r * DIAG_LD + i] = x[r];
+  __syncthreads();
+  for (int e = i; e < TILE * TILE; e += TILE) Tkk[(int64_t)(e >> 6) * npad + (e & 63)] = Ls[(e >> 6) * DIAG_LD + (e & 63)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -648,11 +652,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   }
   const int d = kd.d, nk = kd.nkern;
   const int nacc = nk * d + nk + 2;
-  for (int e = tid; e < nacc; e += 256) {
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int e = warp; e < nacc; e += 8) {  // one warp per slot, lanes stride over tiles (fixed order: deterministic)
     double s = 0.0;
     const double* gp = ws.gpart + (int64_t)b * ntiles * MAXACC + e;
-    for (int tI = 0; tI < ntiles; tI++) s += gp[(int64_t)tI * MAXACC];
-    slots[e] = s;
+    for (int tI = lane; tI < ntiles; tI += 32) s += gp[(int64_t)tI * MAXACC];
+    s = warp_sum(s);
+    if (lane == 0) slots[e] = s;
   }
   __syncthreads();
   for (int e = tid; e < nk * d; e += 256) gr[kd.off_l + e] = -slots[e] / th[kd.off_l + e];
@@ -663,19 +669,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   }
   // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p.  One warp per (dimension, parameter)
   // pair: lanes stride over n, one shuffle reduction, no block-level barrier.
-  const int warp = tid >> 5, lane = tid & 31;
   if (kd.n_iw > 0) {
     const int nb = npad / TILE;
+    // G[n][m] = sum over source tiles, reduced once into slab 0
+    double* G = ws.gxpart + (int64_t)b * nb * npad * d;
+    for (int e = tid; e < N * d; e += 256) {
+      double gsum = 0.0;
+      for (int s = 0; s < nb; s++) gsum += G[(int64_t)s * npad * d + e];
+      G[e] = gsum;
+    }
+    __syncthreads();
     int poff = 0;
     for (int m = 0; m < d; m++) {
       const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;
       for (int q = warp; q < np; q += 8) {
         double acc = 0.0;
-        for (int n = lane; n < N; n += 32) {
-          double gsum = 0.0;
-          for (int s = 0; s < nb; s++) gsum += ws.gxpart[(((int64_t)b * nb + s) * npad + n) * d + m];
-          acc += gsum * ws.dxw[(((int64_t)b * npad + n) * d + m) * MAXWP + q];
-        }
+        for (int n = lane; n < N; n += 32)
+          acc += G[(int64_t)n * d + m] * ws.dxw[(((int64_t)b * npad + n) * d + m) * MAXWP + q];
         acc = warp_sum(acc);
         if (lane == 0) gr[kd.off_iw + poff + q] = acc;
       }

@@ -84,6 +84,21 @@ class GPEngine:
                 pass
             self._h = None
 
+    def set_streams(self, max_groups):
+        if self.lib.avn_gp_set_streams(self._h, int(max_groups)) != 0:
+            raise GPError(_lib.last_error())
+
+    def set_profiling(self, enable=True):
+        if self.lib.avn_gp_set_profiling(self._h, 1 if enable else 0) != 0:
+            raise GPError(_lib.last_error())
+
+    def phase_ms(self):
+        """elapsed milliseconds per phase of the most recent call (synchronises on its last event)."""
+        out = (C.c_double * len(_lib.PHASES))()
+        if self.lib.avn_gp_phase_ms(self._h, out) != 0:
+            raise GPError(_lib.last_error())
+        return dict(zip(_lib.PHASES, list(out)))
+
     # -- layout helpers ----------------------------------------------------------------------
     def offsets(self):
         o, p = {}, 0

@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Benchmark of the GP inner loop (BASELINE.json metric: GP loglik+grad evals/s over batched hypers,
+and predict pts/s) on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Headline workload (config.workload): BASELINE.json configs[1] -- N=2000, d=8 ARD Matern-5/2 GP with
+learnable input (uniform -> kumaraswamy per dimension) and output (log -> sal -> meanstd) warps, P = 30
+hyperparameters; one "step" = one log-likelihood + gradient evaluation for a batch of B hyperparameter
+samples per GPU (synthetic LHC data, seed 202).  Samples are independent units: with N GPUs
+every rank evaluates its own B samples (weak scaling) and the per-shard likelihoods/gradients are
+all-gathered over NCCL inside the timed region.
+
+The JSON line also carries: `e2e` (same metric through GPEngine with HOST buffers, copies timed),
+`roofline` (dominant kernel vs the FP64 tensor peak measured in this run), `cpu_baseline` (the NumPy/SciPy
+oracle timed on the host cores), and `extra` (config 3 batched chains and config 4 predict pts/s).
+`--impl reference` times the oracle port alone (the reference's own GP path needs PyMC, which cannot be
+installed offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workloads
+# ------------------------------------------------------------------------------------------------
+def lhc(n, d, seed):
+    from scipy.stats import qmc
+    return qmc.LatinHypercube(d=d, seed=seed).random(n)
+
+
+def workload_c2(seed=202, N=2000, d=8):
+    from oracle.gp_oracle import ModelSpec
+    rng = np.random.default_rng(seed)
+    X = lhc(N, d, seed)
+    a = np.linspace(0.5, 2.0, d)
+    y = np.exp(np.sum(np.sin(2 * np.pi * a * X), axis=1) / d + 0.5 * X[:, 0] * X[:, 1]) + 0.01 * rng.normal(size=N)
+    spec = ModelSpec(nx=d, kerns=['Matern52'], noise=True,
+                     xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * d, ywarp=['logarithm', 'sal', 'meanstd'])
+    o = spec.offsets()
+    th = np.zeros(o['P'])
+    th[o['gv']] = 1e-4
+    th[o['l']:o['l'] + d] = 0.7
+    th[o['kv']] = 1.5
+    th[o['iw']:o['iw'] + 2 * d] = 1.0
+    th[o['cw']:o['cw'] + 4] = [0.0, 1.0, 0.0, 1.0]
+    return spec, X, y, th
+
+
+def workload_c3(seed=303, N=1000, d=6):
+    from oracle.gp_oracle import ModelSpec
+    rng = np.random.default_rng(seed)
+    X = lhc(N, d, seed)
+    a = np.linspace(0.5, 2.0, d)
+    y = np.sum(np.sin(2 * np.pi * a * X), axis=1) + 0.05 * rng.normal(size=N)
+    y = (y - y.mean()) / y.std()
+    spec = ModelSpec(nx=d, kerns=['RBF'], noise=True)
+    th = np.concatenate([[2e-3], 0.6 * np.ones(d), [1.5]])
+    return spec, X, y, th
+
+
+def workload_c4(seed=404, N=8192, d=10):
+    from oracle.gp_oracle import ModelSpec
+    rng = np.random.default_rng(seed)
+    X = lhc(N, d, seed)
+    y = np.sin(X @ np.linspace(0.5, 2.0, d)) + 0.01 * rng.normal(size=N)
+    y = (y - y.mean()) / y.std()
+    spec = ModelSpec(nx=d, kerns=['Matern52'], noise=True)
+    th = np.concatenate([[1e-4], np.ones(d), [1.5]])
+    return spec, X, y, th
+
+
+def theta_cloud(th, B, seed, scale=0.1):
+    rng = np.random.default_rng(seed)
+    return th[None, :] * np.exp(scale * rng.normal(size=(B, len(th))))
+
+
+def flops_ll(N, d):
+    """algorithmic FP64 flops of one loglik+grad evaluation."""
+    return N ** 3 + (3 * d + 9) * N ** 2
+
+
+def flops_kinv_grad(N, d):
+    """algorithmic flops of the dominant kernel per sample: K^-1 tiles from T (N^3/3) + gradient contractions."""
+    return N ** 3 / 3.0 + (3 * d + 4) * N ** 2 / 2.0
+
+
+def flops_predict(N, d, deg=8):
+    return N ** 2 + (3 * d + 14) * N + 40 * deg
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        info = [i for i in threadpool_info() if i.get('user_api') == 'blas']
+        if info:
+            return int(info[0]['num_threads']), info[0].get('internal_api', '?')
+    except Exception:
+        pass
+    return os.cpu_count(), '?'
+
+
+def cpu_baseline_ll(spec, X, y, thetas, budget_s=12.0, max_evals=64):
+    """oracle loglik+grad timed on the host cores over a bounded sample of the same hyperparameter batch."""
+    from oracle import gp_oracle as go
+    go.loglik(spec, thetas[0], X, y)  # warm BLAS
+    t0 = time.perf_counter()
+    n = 0
+    while n < min(len(thetas), max_evals):
+        go.loglik(spec, thetas[n], X, y, want_grad=True)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import gp_oracle as go
+    spec, X, y, th = workload_c2()
+    thetas = theta_cloud(th, max(args.steps + args.warmup, 4), seed=202)
+    cores, api = blas_threads()
+    per_step = 1  # one evaluation per step: ~1-2 s of multi-threaded LAPACK at N=2000
+    for w in range(args.warmup):
+        go.loglik(spec, thetas[w % len(thetas)], X, y)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        go.loglik(spec, thetas[(args.warmup + s) % len(thetas)], X, y, want_grad=True)
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step / dt
+    line = {
+        'impl': 'reference', 'metric': 'gp_loglik_grad_evals_per_s', 'value': v, 'unit': 'evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'c2: N=2000 d=8 ARD Matern52 + learnable x/y warps, P=30', 'evals_per_step': per_step},
+        'cpu_baseline': {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'blas': api,
+                         'sample': f'{args.steps} sequential oracle loglik+grad evaluations of the c2 model '
+                                   f'(NumPy/SciPy restatement of the PyMC path; PyMC itself is not installable offline)'},
+        'e2e': {'value': v, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='hyperparameter samples per GPU per step (c2)')
+    ap.add_argument('--streams', type=int, default=4, help='concurrent sample groups inside one call')
+    ap.add_argument('--no-extra', action='store_true', help='skip the c3 / c4 side measurements')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import cases
+    from andvaranaut_b200.gp import GPEngine
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- FP64 tensor peak of this GPU (cuBLAS DGEMM, plumbing only) -------------------------------
+    def dgemm_peak(n=8192, reps=4):
+        a = torch.randn(n, n, dtype=torch.float64, device=dev)
+        b = torch.randn(n, n, dtype=torch.float64, device=dev)
+        torch.matmul(a, b)
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+    p64 = dgemm_peak()
+
+    # ---- headline: c2 batched loglik+grad ----------------------------------------------------------
+    spec, X, y, th = workload_c2()
+    N, d, P = X.shape[0], X.shape[1], len(th)
+    B = args.batch
+    eng = GPEngine(**cases.engine_args(spec), device=dev)
+    eng.set_data(X, y)
+    eng.set_streams(args.streams)
+    thetas = theta_cloud(th, B * world, seed=202)[rank * B:(rank + 1) * B]
+    theta_dev = torch.as_tensor(thetas, device=dev)
+    out = (torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, P, dtype=torch.float64, device=dev),
+           torch.empty(B, dtype=torch.int32, device=dev))
+    gathered = torch.empty(world * B, 1 + P, dtype=torch.float64, device=dev) if world > 1 else None
+    packed = torch.empty(B, 1 + P, dtype=torch.float64, device=dev)
+
+    def step():
+        ll, grad, info = eng.loglik_grad(theta_dev, out=out)
+        if world > 1:
+            packed[:, 0] = ll
+            packed[:, 1:] = grad
+            dist.all_gather_into_tensor(gathered, packed)
+        return ll
+
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = int(eng.launches)
+    barrier()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    assert int(out[2].abs().sum()) == 0, 'non-PD sample in the benchmark batch'
+
+    # ---- e2e: host buffers through the public engine call -------------------------------------------
+    th_host = torch.as_tensor(thetas).pin_memory()
+    ll_host = torch.empty(B, dtype=torch.float64).pin_memory()
+    g_host = torch.empty(B, P, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        ll, grad, info = eng.loglik_grad(th_host.to(dev, non_blocking=True), out=out)
+        ll_host.copy_(ll, non_blocking=True)
+        g_host.copy_(grad, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_value = world * B / (e2e_ms * 1e-3)
+
+    # ---- per-phase timing of the same step (separate, untimed repetitions) --------------------------
+    eng.set_profiling(True)
+    phases = {}
+    reps = 3
+    for _ in range(reps):
+        eng.loglik_grad(theta_dev, out=out)
+        pm = eng.phase_ms()
+        for k, v in pm.items():
+            phases[k] = phases.get(k, 0.0) + v / reps
+    eng.set_profiling(False)
+    kg_ms = phases['kinv_grad']
+    kg_flops = B * flops_kinv_grad(N, d)
+    achieved = kg_flops / (kg_ms * 1e-3) / 1e12
+    roofline = {
+        'bound': 'tensor', 'kernel': 'kinv_grad_kernel (K^-1 tiles via DMMA fused with the gradient contraction)',
+        'achieved': achieved, 'peak': p64, 'unit': 'TFLOP/s', 'frac': achieved / p64, 'traffic': None,
+        'peak_source': 'cuBLAS DGEMM fp64 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; '
+                       'DMMA issue peak measured 37.0 TF, profiles/r01_microbench_fp64.jsonl)',
+        'algorithmic_flops_per_launch': kg_flops, 'kernel_ms': kg_ms,
+        'step_frac': B * flops_ll(N, d) / (ms_per_step * 1e-3) / 1e12 / p64,
+        'phase_ms': {k: round(v, 4) for k, v in phases.items() if v > 0},
+    }
+
+    line = {
+        'metric': 'gp_loglik_grad_evals_per_s', 'value': value, 'unit': 'evals/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': f'c2: N={N} d={d} ARD Matern52 + learnable input (uniform,kumaraswamy) and output '
+                               f'(log,sal,meanstd) warps, P={P}; B={B} hyperparameter samples per GPU per step',
+                   'batch_per_gpu': B, 'parallelism': f'{world} x independent hyper batches, all_gather of [B,1+P]',
+                   'l2': f'working set {eng._ws.numel() / 2**30:.1f} GiB per GPU, far larger than the 126 MB L2'},
+        'clocks': clk.summary(),
+        'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(B * P * 8),
+                'd2h_bytes_per_step': int(B * (1 + P) * 8), 'ms_per_step': e2e_ms},
+        'gpu_launches': launches_per_step * args.steps,
+        'roofline': roofline,
+    }
+
+    # ---- side measurements: config 3 and config 4 ---------------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        # c3: 512 chains x N=1000, d=6, sharded over the ranks (strong scaling by definition of the config)
+        spec3, X3, y3, th3 = workload_c3()
+        B3 = 512 // world
+        eng3 = GPEngine(**cases.engine_args(spec3), device=dev)
+        eng3.set_data(X3, y3)
+        eng3.set_streams(args.streams)
+        t3 = torch.as_tensor(theta_cloud(th3, 512, seed=303)[rank * B3:(rank + 1) * B3], device=dev)
+        for _ in range(3):
+            o3 = eng3.loglik_grad(t3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k3 = max(3, args.steps // 2)
+        e0.record()
+        for _ in range(k3):
+            o3 = eng3.loglik_grad(t3)
+        e1.record()
+        barrier()
+        ms3 = max_over_ranks(e0.elapsed_time(e1)) / k3
+        extra['c3_mcmc_chains'] = {'metric': 'gp_loglik_grad_evals_per_s', 'value': 512 / (ms3 * 1e-3), 'unit': 'evals/s',
+                                   'ms_per_step': ms3, 'workload': '512 chains x N=1000 d=6 RBF, one ll+grad per chain',
+                                   'scaling': 'strong', 'frac_of_fp64_peak': 512 * flops_ll(1000, 6) / (ms3 * 1e-3) / 1e12 / (p64 * world),
+                                   'nonpd': int((o3[2] != 0).sum())}
+        del eng3
+        # c4: predict pts/s, N=8192 d=10, test blocks sharded (weak: M_sub points per GPU per step)
+        spec4, X4, y4, th4 = workload_c4()
+        eng4 = GPEngine(**cases.engine_args(spec4), device=dev)
+        eng4.set_data(X4, y4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng4.factorize(th4)
+        e0.record()
+        info4 = eng4.factorize(th4)
+        e1.record()
+        e1.synchronize()
+        fact_ms = e0.elapsed_time(e1)
+        Msub = 148 * 128 * 4
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(405 + rank)
+        Xs = torch.rand(Msub, 10, dtype=torch.float64, device=dev, generator=gen)
+        epi = GPEngine.make_epilogue(mode='revert', deg=8, yrev=[(0, -1, (0.0, 1.0, 0.0, 0.0))])
+        eng4.predict(Xs, epilogue=epi)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k4 = 2
+        e0.record()
+        for _ in range(k4):
+            mu4, var4 = eng4.predict(Xs, epilogue=epi)
+        e1.record()
+        barrier()
+        ms4 = max_over_ranks(e0.elapsed_time(e1)) / k4
+        extra['c4_predict'] = {'metric': 'gp_predict_points_per_s', 'value': world * Msub / (ms4 * 1e-3), 'unit': 'pts/s',
+                               'ms_per_step': ms4, 'points_per_gpu_per_step': Msub,
+                               'workload': 'N=8192 d=10 Matern52, mean+variance+GH(8) reversion; 10M-point job streamed '
+                                           f'in blocks of {Msub} per GPU', 'scaling': 'weak',
+                               'frac_of_fp64_peak': world * Msub * flops_predict(8192, 10) / (ms4 * 1e-3) / 1e12 / (p64 * world),
+                               'factorize_ms': fact_ms, 'info': int(info4[0])}
+        line['extra'] = extra
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores, api = blas_threads()
+        v, n, dt = cpu_baseline_ll(spec, X, y, thetas)
+        line['cpu_baseline'] = {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'blas': api,
+                                'sample': f'{n} of the {B} hyperparameter samples of one step, sequential, all BLAS threads '
+                                          f'({dt:.1f} s); oracle = NumPy/SciPy restatement of the PyMC path'}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -115,6 +115,10 @@ int avn_gp_workspace_layout(const avn_gp* gp, int64_t B, avn_ws_layout* out);
 int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B, double* ll_dev, double* grad_dev,
                        int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Independent samples of one avn_gp_loglik_grad call are split into up to max_groups (1..8, default 4) groups that
+ * run concurrently on library-owned streams, forked from and joined back into the caller's stream. */
+int avn_gp_set_streams(avn_gp* gp, int max_groups);
+
 /* covariance build alone (K + (gv+jitter) I, lower block-triangle valid), K [B,npad,npad] */
 int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
                void* stream);
@@ -132,6 +136,16 @@ int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* Xs_dev, int6
 
 /* introspection used by bench.py: number of kernel launches issued by the last call on this handle */
 int64_t avn_gp_last_launch_count(const avn_gp* gp);
+
+/* phase timing (off by default).  When enabled, avn_gp_loglik_grad / avn_gp_factorize / avn_gp_predict record
+ * CUDA events on the caller's stream around each phase; avn_gp_phase_ms synchronises on the last event and
+ * returns the elapsed milliseconds of the most recent call, indexed by avn_phase. */
+enum avn_phase {
+  AVN_PH_WARP = 0, AVN_PH_COV = 1, AVN_PH_POTRF = 2, AVN_PH_TRSV = 3, AVN_PH_TRTRI = 4, AVN_PH_ALPHA = 5,
+  AVN_PH_KINV_GRAD = 6, AVN_PH_FINALIZE = 7, AVN_PH_KXS = 8, AVN_PH_PREDICT_VAR = 9, AVN_PH_COUNT = 10
+};
+int avn_gp_set_profiling(avn_gp* gp, int enable);
+int avn_gp_phase_ms(avn_gp* gp, double* out_ms /* [AVN_PH_COUNT] */);
 
 #ifdef __cplusplus
 }
