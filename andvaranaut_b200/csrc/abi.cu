@@ -357,6 +357,38 @@ static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& 
   return p;
 }
 
+template <int KIND, bool GX>
+static int launch_kinv_fast_t(dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd, int N, int npad,
+                              const double* theta, const WsPtrs& W) {
+  static size_t opted = 0;
+  if (smem > opted) {
+    cudaError_t e = opt_in_smem(kinv_grad_fast_kernel<KIND, GX>, smem);
+    if (e != cudaSuccess) return fail_cuda("kinv_grad_fast smem opt-in", e);
+    opted = smem;
+  }
+  kinv_grad_fast_kernel<KIND, GX><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, N, npad, theta, W.t, W.alpha, W.xw, W.xs, W.x2,
+                                                                        W.gpart, W.gxpart);
+  return 0;
+}
+
+static int launch_kinv_fast(avn_gp* gp, int kind, bool gx, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd,
+                            int N, int npad, const double* theta, const WsPtrs& W) {
+  (void)gp;
+#define AVN_DISPATCH(K)                                                                     \
+  case K:                                                                                   \
+    return gx ? launch_kinv_fast_t<K, true>(grid, smem, st, kd, N, npad, theta, W)          \
+              : launch_kinv_fast_t<K, false>(grid, smem, st, kd, N, npad, theta, W);
+  switch (kind) {
+    AVN_DISPATCH(AVN_RBF)
+    AVN_DISPATCH(AVN_MATERN52)
+    AVN_DISPATCH(AVN_MATERN32)
+    AVN_DISPATCH(AVN_EXPONENTIAL)
+    AVN_DISPATCH(AVN_RATQUAD)
+  }
+#undef AVN_DISPATCH
+  return fail("launch_kinv_fast: unknown kernel kind");
+}
+
 // the whole evaluation for samples [b0, b0+Bg) on one stream
 static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll, double* grad, int32_t* info,
                         const WsPtrs& W, const avn_ws_layout& L, cudaStream_t st) {
@@ -382,12 +414,21 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
       attr_done = true;
     }
     Phase ph(gp, AVN_PH_KINV_GRAD, st);
-    if (gp->has_xwarp)
-      kinv_grad_kernel<true><<<dim3((unsigned)ntiles, (unsigned)Bg), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
+    const dim3 grid((unsigned)ntiles, (unsigned)Bg);
+    if (kd.nkern == 1) {
+      // single-kernel model: DMMA epilogue specialised on the kernel kind
+      const KinvFastLayout lay(kd.d);
+      size_t smem = (size_t)lay.total * 8;
+      if (smem < KinvG2::SMEM_BYTES) smem = KinvG2::SMEM_BYTES;
+      rc = launch_kinv_fast(gp, kd.kern[0], gp->has_xwarp, grid, smem, st, kd, (int)gp->N, (int)npad, theta, W);
+      if (rc) return rc;
+    } else if (gp->has_xwarp) {
+      kinv_grad_kernel<true><<<grid, KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
           kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
-    else
-      kinv_grad_kernel<false><<<dim3((unsigned)ntiles, (unsigned)Bg), KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
+    } else {
+      kinv_grad_kernel<false><<<grid, KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
           kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, W.xw, W.gpart, W.gxpart);
+    }
     LAUNCH_CHECK("kinv_grad_kernel");
   }
   Phase phf(gp, AVN_PH_FINALIZE, st);

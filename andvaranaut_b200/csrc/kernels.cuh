@@ -94,7 +94,7 @@ __device__ __forceinline__ void tri_index(int t, int& i, int& j) {
 __global__ void __launch_bounds__(256) cov_kernel(KernDesc kd, int N, int npad, const double* __restrict__ theta,
                                                   const double* __restrict__ xs_all, const double* __restrict__ x2_all,
                                                   double* __restrict__ Kout) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ HypS hyp;
   const int b = blockIdx.y, tid = threadIdx.x;
   int ti, tj;
@@ -102,17 +102,19 @@ __global__ void __launch_bounds__(256) cov_kernel(KernDesc kd, int N, int npad, 
   const int i0 = ti * TILE, j0 = tj * TILE;
   const int d = kd.d, nk = kd.nkern;
   load_hyp(hyp, kd, theta + (int64_t)b * kd.P);
-  // smem: xi[nk][64][d], xj[nk][64][d], x2i[nk][64], x2j[nk][64]
+  // smem, dimension-major so that a thread's 4 rows / 4 columns are one 32-byte read:
+  //   xi[nk][d][64], xj[nk][d][64], x2i[nk][64], x2j[nk][64]
   double* sxi = smem;
-  double* sxj = sxi + nk * TILE * d;
-  double* s2i = sxj + nk * TILE * d;
+  double* sxj = sxi + nk * d * TILE;
+  double* s2i = sxj + nk * d * TILE;
   double* s2j = s2i + nk * TILE;
   for (int k = 0; k < nk; k++) {
     const double* xs = xs_all + ((int64_t)b * nk + k) * npad * d;
     const double* x2 = x2_all + ((int64_t)b * nk + k) * npad;
     for (int e = tid; e < TILE * d; e += 256) {
-      sxi[k * TILE * d + e] = xs[(int64_t)i0 * d + e];
-      sxj[k * TILE * d + e] = xs[(int64_t)j0 * d + e];
+      const int r = e / d, m = e % d;
+      sxi[(k * d + m) * TILE + r] = xs[(int64_t)i0 * d + e];
+      sxj[(k * d + m) * TILE + r] = xs[(int64_t)j0 * d + e];
     }
     if (tid < TILE) {
       s2i[k * TILE + tid] = x2[i0 + tid];
@@ -123,25 +125,48 @@ __global__ void __launch_bounds__(256) cov_kernel(KernDesc kd, int N, int npad, 
   const int tx = tid & 15, ty = tid >> 4;
   double* Kb = Kout + (int64_t)b * npad * npad;
   const double dadd = hyp.gv + kd.jitter;
+  double out[4][4];
+  for (int k = 0; k < nk; k++) {
+    double dot[4][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) dot[rr][cc] = 0.0;
+    for (int m = 0; m < d; m++) {
+      const double2* pi = reinterpret_cast<const double2*>(sxi + (k * d + m) * TILE + ty * 4);
+      const double2* pj = reinterpret_cast<const double2*>(sxj + (k * d + m) * TILE + tx * 4);
+      const double2 a0 = pi[0], a1 = pi[1], b0 = pj[0], b1 = pj[1];
+      const double xi[4] = {a0.x, a0.y, a1.x, a1.y}, xj[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) dot[rr][cc] = fma(xi[rr], xj[cc], dot[rr][cc]);   // sequential in m
+    }
+    const int kind = kd.kern[k];
+    const double kvk = hyp.kv[k];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        double r2 = __dadd_rn(__dmul_rn(-2.0, dot[rr][cc]), __dadd_rn(s2i[k * TILE + ty * 4 + rr], s2j[k * TILE + tx * 4 + cc]));
+        r2 = r2 > 0.0 ? r2 : 0.0;
+        const double v = __dmul_rn(kvk, kern_val_only(kind, r2, hyp.alpha));
+        if (k == 0) out[rr][cc] = v;
+        else out[rr][cc] = (kd.op[k - 1] == AVN_ADD) ? __dadd_rn(out[rr][cc], v) : __dmul_rn(out[rr][cc], v);
+      }
+  }
 #pragma unroll
   for (int rr = 0; rr < 4; rr++) {
-    const int r = ty * 4 + rr, I = i0 + r;
-    double out[4];
+    const int I = i0 + ty * 4 + rr;
 #pragma unroll
     for (int cc = 0; cc < 4; cc++) {
-      const int c = tx * 4 + cc, J = j0 + c;
-      double v;
-      if (I >= N || J >= N) {
-        v = (I == J) ? 1.0 : 0.0;
-      } else {
-        v = cov_fold(kd, hyp, sxi + r * d, TILE * d, s2i + r, TILE, sxj + c * d, TILE * d, s2j + c, TILE);
-        if (I == J) v += dadd;
-      }
-      out[cc] = v;
+      const int J = j0 + tx * 4 + cc;
+      if (I >= N || J >= N) out[rr][cc] = (I == J) ? 1.0 : 0.0;
+      else if (I == J) out[rr][cc] += dadd;
     }
     double2* dst = reinterpret_cast<double2*>(Kb + (int64_t)I * npad + j0 + tx * 4);
-    dst[0] = make_double2(out[0], out[1]);
-    dst[1] = make_double2(out[2], out[3]);
+    dst[0] = make_double2(out[rr][0], out[rr][1]);
+    dst[1] = make_double2(out[rr][2], out[rr][3]);
   }
 }
 
@@ -835,3 +860,5 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc k
 }
 
 }  // namespace avn
+
+#include "kinv_fast.cuh"
