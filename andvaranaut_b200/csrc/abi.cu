@@ -227,7 +227,10 @@ extern "C" int avn_gp_workspace_layout(const avn_gp* gp, int64_t B, avn_ws_layou
 
 template <typename K>
 static cudaError_t opt_in_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  // ask for the full shared-memory carveout so that several CTAs fit on one SM
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 #define LAUNCH_CHECK(name)                                  \
@@ -260,6 +263,10 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
   return 0;
 }
 
+// the trtri epilogue stages two 64x68 tiles in the (aliased) pipeline buffers
+static const size_t kTrtriSmem =
+    TrtriG::SMEM_BYTES > (size_t)2 * TILE * (TILE + SPAD) * 8 ? TrtriG::SMEM_BYTES : (size_t)2 * TILE * (TILE + SPAD) * 8;
+
 // Cholesky K -> L in place (kl), diagonal-block inverses into t, then the rest of T = L^-1
 static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* info, int64_t npad, bool want_inverse,
                       cudaStream_t st) {
@@ -270,7 +277,7 @@ static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* inf
   if (!attr_done) {
     cudaError_t e = opt_in_smem(potrf_update_kernel<BM>, PG::SMEM_BYTES);
     if (e == cudaSuccess) e = opt_in_smem(potrf_panel_kernel<BM>, PG::SMEM_BYTES);
-    if (e == cudaSuccess) e = opt_in_smem(trtri_row_kernel, TrtriG::SMEM_BYTES);
+    if (e == cudaSuccess) e = opt_in_smem(trtri_row_kernel, kTrtriSmem);
     if (e != cudaSuccess) return fail_cuda("factor smem opt-in", e);
     attr_done = true;
   }
@@ -294,7 +301,7 @@ static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* inf
   if (want_inverse) {
     Phase ph(gp, AVN_PH_TRTRI, st);
     for (int i = 1; i < nb; i++) {
-      trtri_row_kernel<<<dim3(i, (unsigned)B), TrtriG::NTHREADS, TrtriG::SMEM_BYTES, st>>>(kl, t, (int)npad, i);
+      trtri_row_kernel<<<dim3(i, (unsigned)B), TrtriG::NTHREADS, kTrtriSmem, st>>>(kl, t, (int)npad, i);
       LAUNCH_CHECK("trtri_row_kernel");
     }
   }

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) cov_kernel(KernDesc kd, int N, int npad, 
 // ------------------------------------------------------------------------------------------------
 template <int BM>
 struct PotrfCfg {
-  using G = TileGemm<BM, 64, 16, 32, 32, 4, false, false>;
+  using G = TileGemm<BM, 64, 16, 32, 32, 3, false, false>;  // 3 stages: 92 KB -> 2 CTAs/SM
 };
 
 template <int BM>
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ La
 // K2b: T = L^-1, block row i:  T[i,j] = -T[i,i] * sum_{k=j}^{i-1} L[i,k] T[k,j]   (j < i)
 // grid (i, B): one 64x64 output tile per CTA, 128 threads.
 // ------------------------------------------------------------------------------------------------
-using TrtriG = TileGemm<64, 64, 16, 32, 32, 4, false, true>;
+using TrtriG = TileGemm<64, 64, 16, 32, 32, 3, false, true>;  // 3 stages: 57 KB -> 3 CTAs/SM
 
 template <int LDA, int LDB>
 __device__ __forceinline__ void smem_gemm64(double (&acc)[4][4][2], const double* sA,

@@ -482,15 +482,21 @@ class wgp:
     def rev_program(self):
         """Frozen program (all coefficients constant), evaluated right-to-left by the predict
         epilogue for the Gauss-Hermite reversion (gpmcmc.py:551)."""
-        prog = []
-        for st in self.warpings:
-            op = STAGES[st.name][0]
-            if isinstance(st, affine):
-                op = OP_AFFINE_CONST
-            elif op == OP_BOXCOX:
-                op = OP_BOXCOX_CONST
-            c = [0.0] * 4
-            cc = st.coeffs()
-            c[:len(cc)] = cc
-            prog.append((op, -1, tuple(c)))
-        return prog
+        return [frozen_stage(st) for st in self.warpings]
+
+
+def frozen_stage(st):
+    """(opcode, -1, constants) of one differentiable stage with its coefficients frozen; None if the object is
+    not one of the device-evaluable stages."""
+    if not isinstance(st, _stage):
+        return None
+    if isinstance(st, affine):
+        op = OP_AFFINE_CONST
+    elif isinstance(st, boxcox):
+        op = OP_BOXCOX_CONST
+    else:
+        op = st.op
+    c = [0.0] * 4
+    cc = st.coeffs()
+    c[:len(cc)] = cc
+    return (op, -1, tuple(c))
