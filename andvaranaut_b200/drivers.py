@@ -43,7 +43,8 @@ class Posterior:
         self.n_calls += 1
         lp, glp = self.space.prior(theta)
         val = ll + lp
-        grad = self.space.grad_theta_to_z(gll + glp, dxdz)
+        with np.errstate(all='ignore'):
+            grad = self.space.grad_theta_to_z(gll + glp, dxdz)
         if jacobian:
             val = val + ljac
             grad = grad + dljac
@@ -217,7 +218,8 @@ def sample(post, draws=1000, tune=1000, chains=4, seed=None, target_accept=0.8, 
                 alive &= ~dead
                 gn[dead] = 0.0
             p = p + 0.5 * eps[:, None] * gn
-        h1 = -lpn + 0.5 * np.sum(p * p * inv_mass, axis=1)
+        with np.errstate(all='ignore'):
+            h1 = -lpn + 0.5 * np.sum(p * p * inv_mass, axis=1)
         with np.errstate(over='ignore', invalid='ignore'):
             acc = np.where(alive & np.isfinite(h1), np.minimum(1.0, np.exp(h0 - h1)), 0.0)
         take = rng.uniform(size=chains) < acc

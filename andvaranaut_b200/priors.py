@@ -45,6 +45,10 @@ class _Block:
 
     def backward(self, z):
         """x(z), dx/dz, log|dx/dz|, d log|dx/dz| / dz"""
+        with np.errstate(all='ignore'):      # far-out proposals of the samplers overflow harmlessly to inf/0
+            return self._backward(z)
+
+    def _backward(self, z):
         if self.transform == 'log':
             x = np.exp(z)
             return x, x, z, np.ones_like(z)
@@ -58,6 +62,10 @@ class _Block:
 
     # -- prior log density in the constrained space and its derivative ----------------------
     def logp(self, x):
+        with np.errstate(all='ignore'):
+            return self._logp(x)
+
+    def _logp(self, x):
         f, a = self.family, self.args
         if f == 'lognormal':
             mu, sg = a
