@@ -289,7 +289,7 @@ static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* inf
       potrf_update_kernel<BM><<<dim3((rows + BM - 1) / BM, (unsigned)B), PG::NTHREADS, PG::SMEM_BYTES, st>>>(kl, (int)npad, k);
       LAUNCH_CHECK("potrf_update_kernel");
     }
-    potrf_diag_kernel<<<(unsigned)B, TILE, 0, st>>>(kl, t, (int)npad, k, info);
+    potrf_diag_kernel<<<(unsigned)B, 256, 0, st>>>(kl, t, (int)npad, k, info);
     LAUNCH_CHECK("potrf_diag_kernel");
     if (k + 1 < nb) {
       int rows = (nb - k - 1) * TILE;

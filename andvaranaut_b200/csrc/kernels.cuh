@@ -238,73 +238,131 @@ __global__ void __launch_bounds__(PotrfCfg<BM>::G::NTHREADS) potrf_panel_kernel(
     }
 }
 
-// diagonal block: unblocked Cholesky + triangular inverse.  grid (B), 64 threads.
-// Thread i keeps row i of the block in registers (fully unrolled, static indexing); each of the 64
-// column steps publishes the scaled column through shared memory (2 barriers of 2 warps) and every
-// thread applies the rank-1 update to its row.  The inverse is computed column-per-thread from the
-// shared copy of L (all lanes read the same L element: broadcast, no conflicts).
-constexpr int DIAG_LD = TILE + 2;
-__global__ void __launch_bounds__(TILE) potrf_diag_kernel(double* __restrict__ Lall, double* __restrict__ Tall,
-                                                          int npad, int kblk, int32_t* __restrict__ info) {
-  __shared__ __align__(16) double Ls[TILE * DIAG_LD];
-  __shared__ __align__(16) double col[TILE];
+// diagonal block: unblocked Cholesky + triangular inverse.  grid (B), 256 threads.
+// Thread (ty, tx) of a 16 x 16 grid keeps the 4 x 4 sub-block (rows 4ty.., cols 4tx..) in registers; the 64 column
+// steps are fully unrolled (static register indexing, ~40 instructions each so the code stays inside the
+// instruction cache).  Step j: the pivot owner publishes 1/L_jj, the owners of column j scale it and publish it,
+// every thread applies the rank-1 update to its sub-block.  The inverse T = L^-1 is the same right-looking sweep
+// on the rows of the identity (row j of T final after step j, then R[i,:] -= L[i,j] T[j,:]).
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lall, double* __restrict__ Tall,
+                                                         int npad, int kblk, int32_t* __restrict__ info) {
+  constexpr int LD = TILE + 2;
+  __shared__ __align__(16) double Ls[TILE * LD];
+  __shared__ __align__(16) double vec[TILE];
+  __shared__ double invd[TILE];
   __shared__ double pivinv;
-  const int b = blockIdx.x, i = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
   double* Lkk = Lall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
   double* Tkk = Tall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
-  // coalesced load through shared memory
-  for (int e = i; e < TILE * TILE; e += TILE) Ls[(e >> 6) * DIAG_LD + (e & 63)] = Lkk[(int64_t)(e >> 6) * npad + (e & 63)];
-  __syncthreads();
-  double a[TILE];
+  double a[4][4];
 #pragma unroll
-  for (int c = 0; c < TILE; c++) a[c] = (c <= i) ? Ls[i * DIAG_LD + c] : 0.0;
-  __syncthreads();
-  double myinv = 1.0;  // 1 / L_ii of this thread's row
+  for (int r = 0; r < 4; r++) {
+    const double2* src = reinterpret_cast<const double2*>(Lkk + (int64_t)(4 * ty + r) * npad + 4 * tx);
+    const double2 v0 = src[0], v1 = src[1];
+    a[r][0] = v0.x; a[r][1] = v0.y; a[r][2] = v1.x; a[r][3] = v1.y;
+  }
+  // ---- Cholesky ----
 #pragma unroll
   for (int j = 0; j < TILE; j++) {
-    if (i == j) {
-      double dj = a[j];
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int jb = j >> 2, jj = j & 3;
+    if (ty == jb && tx == jb) {
+      double dj = a[jj][jj];
       if (!(dj > 0.0)) {  // also catches NaN
         if (info[b] == 0) info[b] = kblk * TILE + j + 1;
         dj = 1.0;
       }
-      const double ljj = sqrt(dj);
-      a[j] = ljj;
-      myinv = 1.0 / ljj;
-      pivinv = myinv;
+      // one reciprocal square root instead of a sqrt followed by a division on the critical path
+      const double inv = rsqrt(dj);
+      a[jj][jj] = dj * inv;
+      pivinv = inv;
+      invd[j] = inv;
     }
     __syncthreads();
-    double lij = 0.0;
-    if (i > j) {
-      lij = a[j] * pivinv;
-      a[j] = lij;
+    if (tx == jb && ty >= jb) {
+      const double inv = pivinv;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int row = 4 * ty + r;
+        double l = 0.0;
+        if (row > j) {
+          l = a[r][jj] * inv;
+          a[r][jj] = l;
+        }
+        vec[row] = l;
+      }
+    } else if (tx == jb && ty < jb) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) vec[4 * ty + r] = 0.0;
     }
-    col[i] = lij;
     __syncthreads();
+    if (tx <= ty && ty >= jb) {
+      const double2 r0 = *reinterpret_cast<const double2*>(&vec[4 * ty]), r1 = *reinterpret_cast<const double2*>(&vec[4 * ty + 2]);
+      const double2 c0 = *reinterpret_cast<const double2*>(&vec[4 * tx]), c1 = *reinterpret_cast<const double2*>(&vec[4 * tx + 2]);
+      const double cr[4] = {r0.x, r0.y, r1.x, r1.y}, cc[4] = {c0.x, c0.y, c1.x, c1.y};
 #pragma unroll
-    for (int c = j + 1; c < TILE; c++) a[c] = fma(-lij, col[c], a[c]);
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (4 * tx + c > j) a[r][c] = fma(-cr[r], cc[c], a[r][c]);   // columns <= j are final
+    }
   }
-  // rows back to shared memory (upper part zero), reciprocal diagonal in col[]
+  // L (lower part) to shared memory and to global
 #pragma unroll
-  for (int c = 0; c < TILE; c++) Ls[i * DIAG_LD + c] = (c <= i) ? a[c] : 0.0;
-  col[i] = myinv;
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) Ls[(4 * ty + r) * LD + 4 * tx + c] = (4 * tx + c <= 4 * ty + r) ? a[r][c] : 0.0;
   __syncthreads();
-  // T = L^-1, thread c owns column c:  x_r = (delta_rc - sum_{k<r} L_rk x_k) / L_rr
-  double x[TILE];
 #pragma unroll
-  for (int r = 0; r < TILE; r++) {
-    double s = (r == i) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < r; k++) s = fma(-Ls[r * DIAG_LD + k], x[k], s);
-    x[r] = s * col[r];
+  for (int r = 0; r < 4; r++) {
+    double2* dst = reinterpret_cast<double2*>(Lkk + (int64_t)(4 * ty + r) * npad + 4 * tx);
+    const double* srow = &Ls[(4 * ty + r) * LD + 4 * tx];
+    dst[0] = make_double2(srow[0], srow[1]);
+    dst[1] = make_double2(srow[2], srow[3]);
   }
-  // write L (coalesced from shared) and T (through shared, then coalesced)
-  for (int e = i; e < TILE * TILE; e += TILE) Lkk[(int64_t)(e >> 6) * npad + (e & 63)] = Ls[(e >> 6) * DIAG_LD + (e & 63)];
-  __syncthreads();
+  // ---- T = L^-1: start from the identity ----
 #pragma unroll
-  for (int r = 0; r < TILE; r++) Ls[r * DIAG_LD + i] = x[r];
-  __syncthreads();
-  for (int e = i; e < TILE * TILE; e += TILE) Tkk[(int64_t)(e >> 6) * npad + (e & 63)] = Ls[(e >> 6) * DIAG_LD + (e & 63)];
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) a[r][c] = (4 * ty + r == 4 * tx + c) ? 1.0 : 0.0;
+#pragma unroll
+  for (int j = 0; j < TILE; j++) {
+    const int jb = j >> 2, jj = j & 3;
+    // row j of T is final once divided by L_jj; publish it (zero right of the diagonal)
+    if (ty == jb) {
+      const double inv = invd[j];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double v = (4 * tx + c <= j) ? a[jj][c] * inv : 0.0;
+        a[jj][c] = v;
+        vec[4 * tx + c] = v;
+      }
+    }
+    __syncthreads();
+    if (tx <= ty && ty >= jb) {
+      const double2 c0 = *reinterpret_cast<const double2*>(&vec[4 * tx]), c1 = *reinterpret_cast<const double2*>(&vec[4 * tx + 2]);
+      const double cc[4] = {c0.x, c0.y, c1.x, c1.y};
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int row = 4 * ty + r;
+        const double lij = (row > j) ? Ls[row * LD + j] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) a[r][c] = fma(-lij, cc[c], a[r][c]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    double2* dst = reinterpret_cast<double2*>(Tkk + (int64_t)(4 * ty + r) * npad + 4 * tx);
+    double o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) o[c] = (4 * tx + c <= 4 * ty + r) ? a[r][c] : 0.0;
+    dst[0] = make_double2(o[0], o[1]);
+    dst[1] = make_double2(o[2], o[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
