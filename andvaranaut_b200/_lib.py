@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libavn_gp.so')
+# AVN_GP_LIB selects an instrumented build of the same library (e.g. -DAVN_FACTOR_PROF); default: the in-tree one
+LIB_PATH = os.environ.get('AVN_GP_LIB') or os.path.join(_HERE, 'libavn_gp.so')
 
 AVN_MAX_D = 16
 AVN_MAX_KERN = 4
@@ -37,7 +38,7 @@ class ModelDesc(C.Structure):
 
 class WsLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ('npad', 'nb', 'xw', 'dxw', 'xs', 'x2', 'z', 'dz', 'wstat', 'kl', 't',
-                                         'beta', 'alpha', 'gpart', 'gxpart', 'total')]
+                                         'beta', 'alpha', 'gpart', 'gxpart', 'fpart', 'fflags', 'total')]
 
 
 class Epilogue(C.Structure):

@@ -28,7 +28,7 @@ struct avn_gp {
   int64_t launches = 0;
   bool has_xwarp = false;
   bool profiling = false;
-  int max_groups = 4;                 // independent sample groups run on internal streams
+  int max_groups = 1;                 // independent sample groups on internal streams (avn_gp_set_streams)
   cudaStream_t gstream[8] = {};
   cudaEvent_t gev[9] = {};            // [0]: fork point on the caller's stream, [1+g]: join of group g
   cudaEvent_t ev[2 * AVN_PH_COUNT] = {};
@@ -199,16 +199,22 @@ static void layout(const avn_gp* gp, int64_t B, avn_ws_layout* L) {
   L->alpha = take(B * npad);
   L->gpart = take(B * ntiles * MAXACC);
   L->gxpart = take(gp->has_xwarp ? B * nb * npad * kd.d : 0);
+  L->fpart = take(B * nb * 2);
+  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], then 8 control words per stream group
+  L->fflags = take((2 * B * nb + 8 * 8 + 1) / 2);
   L->total = off;
 }
 
-static WsPtrs ws_ptrs(const avn_ws_layout& L, void* ws) {
+static WsPtrs ws_ptrs(const avn_ws_layout& L, void* ws, int64_t B) {
   char* base = static_cast<char*>(ws);
   auto at = [&](int64_t o) { return reinterpret_cast<double*>(base + o); };
   WsPtrs p;
   p.xw = at(L.xw); p.dxw = at(L.dxw); p.xs = at(L.xs); p.x2 = at(L.x2); p.z = at(L.z); p.dz = at(L.dz);
   p.wstat = at(L.wstat); p.kl = at(L.kl); p.t = at(L.t); p.beta = at(L.beta); p.alpha = at(L.alpha);
-  p.gpart = at(L.gpart); p.gxpart = at(L.gxpart);
+  p.gpart = at(L.gpart); p.gxpart = at(L.gxpart); p.fpart = at(L.fpart);
+  p.lflag = reinterpret_cast<int32_t*>(base + L.fflags);
+  p.tflag = p.lflag + B * L.nb;
+  p.ctl = p.tflag + B * L.nb;
   return p;
 }
 
@@ -263,68 +269,82 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
   return 0;
 }
 
-// the trtri epilogue stages two 64x68 tiles in the (aliased) pipeline buffers
-static const size_t kTrtriSmem =
-    TrtriG::SMEM_BYTES > (size_t)2 * TILE * (TILE + SPAD) * 8 ? TrtriG::SMEM_BYTES : (size_t)2 * TILE * (TILE + SPAD) * 8;
+// Persistent grid of the factor kernel: as many CTAs as fit on the device at once (3 per SM), never more than tasks.
+static int factor_grid(int64_t total_tasks, int* out) {
+  static int resident = 0;
+  if (!resident) {
+    cudaError_t e = opt_in_smem(factor_kernel, FAC_SMEM_BYTES);
+    if (e != cudaSuccess) return fail_cuda("factor smem opt-in", e);
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES);
+    if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
+    resident = sms * per_sm;
+  }
+  *out = (int)(total_tasks < resident ? total_tasks : resident);
+  return 0;
+}
 
-// Cholesky K -> L in place (kl), diagonal-block inverses into t, then the rest of T = L^-1
-static int run_factor(avn_gp* gp, int64_t B, double* kl, double* t, int32_t* info, int64_t npad, bool want_inverse,
+// Cholesky K -> L in place (kl) and T = L^-1 (t): one persistent dataflow launch (factor.cuh).
+// The caller has zeroed W.lflag / W.tflag / W.ctl on this stream.
+static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int64_t npad, bool want_inverse,
                       cudaStream_t st) {
   const int nb = (int)(npad / TILE);
-  constexpr int BM = 128;
-  using PG = PotrfCfg<BM>::G;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = opt_in_smem(potrf_update_kernel<BM>, PG::SMEM_BYTES);
-    if (e == cudaSuccess) e = opt_in_smem(potrf_panel_kernel<BM>, PG::SMEM_BYTES);
-    if (e == cudaSuccess) e = opt_in_smem(trtri_row_kernel, kTrtriSmem);
-    if (e != cudaSuccess) return fail_cuda("factor smem opt-in", e);
-    attr_done = true;
-  }
+  const int64_t total = B * nb * nb;
+  if (total > 0x7fffffffLL) return fail("run_factor: B * (N/64)^2 exceeds the task counter");
+  int grid = 0;
+  int rc = factor_grid(total, &grid);
+  if (rc) return rc;
+  FactorArgs fa;
+  fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info;
+  fa.lflag = W.lflag; fa.tflag = W.tflag; fa.ctl = W.ctl;
+  fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.want_inverse = want_inverse ? 1 : 0;
+  fa.dgap = (int)((2 * (int64_t)grid + B - 1) / B);
+  fa.prof = nullptr;
+#ifdef AVN_FACTOR_PROF
+  static long long* prof_dev = nullptr;
+  if (!prof_dev) cudaMalloc(&prof_dev, 64);
+  cudaMemsetAsync(prof_dev, 0, 64, st);
+  fa.prof = prof_dev;
+#endif
   {
-  Phase ph(gp, AVN_PH_POTRF, st);
-  for (int k = 0; k < nb; k++) {
-    if (k > 0) {
-      int rows = (nb - k) * TILE;
-      potrf_update_kernel<BM><<<dim3((rows + BM - 1) / BM, (unsigned)B), PG::NTHREADS, PG::SMEM_BYTES, st>>>(kl, (int)npad, k);
-      LAUNCH_CHECK("potrf_update_kernel");
-    }
-    potrf_diag_kernel<<<(unsigned)B, 256, 0, st>>>(kl, t, (int)npad, k, info);
-    LAUNCH_CHECK("potrf_diag_kernel");
-    if (k + 1 < nb) {
-      int rows = (nb - k - 1) * TILE;
-      potrf_panel_kernel<BM><<<dim3((rows + BM - 1) / BM, (unsigned)B), PG::NTHREADS, PG::SMEM_BYTES, st>>>(kl, t, (int)npad, k);
-      LAUNCH_CHECK("potrf_panel_kernel");
-    }
+    Phase ph(gp, AVN_PH_POTRF, st);
+    factor_kernel<<<grid, FAC_THREADS, FAC_SMEM_BYTES, st>>>(fa);
+    LAUNCH_CHECK("factor_kernel");
   }
+#ifdef AVN_FACTOR_PROF
+  {
+    long long h[8];
+    cudaMemcpyAsync(h, prof_dev, 64, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    double tot = 0;
+    for (int q = 0; q < 6; q++) tot += (double)h[q];
+    fprintf(stderr, "[factor prof] grid %d  ticket %.1f%%  wait %.1f%%  gemm %.1f%%  wait_tkk %.1f%%  epilogue %.1f%%  diag %.1f%%  (cycles/CTA %.0f)\n",
+            grid, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / grid);
   }
-  if (want_inverse) {
-    Phase ph(gp, AVN_PH_TRTRI, st);
-    for (int i = 1; i < nb; i++) {
-      trtri_row_kernel<<<dim3(i, (unsigned)B), TrtriG::NTHREADS, kTrtriSmem, st>>>(kl, t, (int)npad, i);
-      LAUNCH_CHECK("trtri_row_kernel");
-    }
+#endif
+  return 0;
+}
+
+// beta = T z (+ partial sums of beta^T beta), alpha = T^T beta
+static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, bool want_alpha, cudaStream_t st) {
+  const dim3 grid((unsigned)(npad / TILE), (unsigned)B);
+  {
+    Phase ph(gp, AVN_PH_TRSV, st);
+    beta_kernel<<<grid, 256, 0, st>>>(W.t, W.z, (int)npad, W.beta, W.fpart);
+    LAUNCH_CHECK("beta_kernel");
+  }
+  if (want_alpha) {
+    Phase ph(gp, AVN_PH_ALPHA, st);
+    alpha_kernel<<<grid, 256, 0, st>>>(W.t, W.beta, (int)npad, W.alpha);
+    LAUNCH_CHECK("alpha_kernel");
   }
   return 0;
 }
 
-static int run_trsv_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, bool want_alpha, cudaStream_t st) {
-  size_t smem = (size_t)(npad + TILE + 32) * 8;
-  if (smem > 48 * 1024) {
-    cudaError_t e = opt_in_smem(trsv_kernel, smem);
-    if (e != cudaSuccess) return fail_cuda("trsv smem", e);
-  }
-  {
-    Phase ph(gp, AVN_PH_TRSV, st);
-    trsv_kernel<<<(unsigned)B, 256, smem, st>>>(W.kl, W.t, W.z, (int)npad, W.beta, W.wstat);
-    LAUNCH_CHECK("trsv_kernel");
-  }
-  if (want_alpha) {
-    Phase ph(gp, AVN_PH_ALPHA, st);
-    alpha_kernel<<<dim3((unsigned)(npad / TILE), (unsigned)B), 256, 0, st>>>(W.t, W.beta, (int)npad, W.alpha);
-    LAUNCH_CHECK("alpha_kernel");
-  }
-  return 0;
+static cudaError_t zero_flags(const WsPtrs& W, int64_t B, int64_t nb, cudaStream_t st) {
+  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(2 * B * nb + 64), st);
 }
 
 extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
@@ -338,7 +358,7 @@ extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  WsPtrs W = ws_ptrs(L, ws_dev);
+  WsPtrs W = ws_ptrs(L, ws_dev, B);
   int rc = run_warp(gp, theta_dev, B, W, L.npad, st);
   if (rc) return rc;
   return run_cov(gp, theta_dev, B, W, L.npad, K_dev, st);
@@ -361,6 +381,9 @@ static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& 
   p.alpha += b0 * npad;
   p.gpart += b0 * ntiles * MAXACC;
   p.gxpart += b0 * nb * npad * kd.d;
+  p.fpart += b0 * nb * 2;
+  p.lflag += b0 * nb;
+  p.tflag += b0 * nb;
   return p;
 }
 
@@ -408,9 +431,9 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
   if (rc) return rc;
   rc = run_cov(gp, theta, Bg, W, npad, W.kl, st);
   if (rc) return rc;
-  rc = run_factor(gp, Bg, W.kl, W.t, info, npad, want_grad, st);
+  rc = run_factor(gp, Bg, W, info, npad, true, st);   // beta = T z needs the inverse also without a gradient
   if (rc) return rc;
-  rc = run_trsv_alpha(gp, Bg, W, npad, want_grad, st);
+  rc = run_beta_alpha(gp, Bg, W, npad, want_grad, st);
   if (rc) return rc;
   if (want_grad) {
     static bool attr_done = false;
@@ -463,13 +486,17 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  WsPtrs W = ws_ptrs(L, ws_dev);
+  WsPtrs W = ws_ptrs(L, ws_dev, B);
   const int P = gp->kd.P;
   // Samples are independent: split them into groups that run the whole sequence on internal streams, so the
   // latency-bound steps of one group (diagonal blocks, short panels, tails) overlap the DMMA-bound steps of
   // another.  Phase timing needs one ordered stream, so profiling forces a single group.
   int G = gp->profiling ? 1 : gp->max_groups;
   if (B < 8 * G) G = (int)(B / 8 > 0 ? B / 8 : 1);
+  {
+    cudaError_t e = zero_flags(W, B, L.nb, st);
+    if (e != cudaSuccess) return fail_cuda("memset flags", e);
+  }
   if (G <= 1) return loglik_group(gp, theta_dev, B, ll_dev, grad_dev, info_dev, W, L, st);
   for (int g = 0; g < G; g++)
     if (!gp->gstream[g]) {
@@ -489,6 +516,7 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
     cudaStream_t gs = gp->gstream[g];
     cudaStreamWaitEvent(gs, gp->gev[0], 0);
     WsPtrs Wg = ws_offset(W, gp, L, b0);
+    Wg.ctl = W.ctl + 8 * g;
     rc = loglik_group(gp, theta_dev + b0 * P, b1 - b0, ll_dev + b0, grad_dev ? grad_dev + b0 * P : nullptr,
                       info_dev + b0, Wg, L, gs);
     cudaEventRecord(gp->gev[1 + g], gs);
@@ -543,14 +571,15 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
   if (gp->has_xwarp || gp->kd.n_cw > 0)
     return fail("avn_gp_factorize: predict works on converted data; bake the warps on the host first (gpmcmc.py:364-399)");
   avn_ws_layout L;
-  layout(gp, 1, &L);
+  const int64_t B = 1;
+  layout(gp, B, &L);
   StateLayout S = state_layout(gp);
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_factorize: workspace too small");
   if (state_bytes < (size_t)S.total) return fail("avn_gp_factorize: state buffer too small");
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  WsPtrs W = ws_ptrs(L, ws_dev);
+  WsPtrs W = ws_ptrs(L, ws_dev, B);
   char* sb = static_cast<char*>(state_dev);
   // T, alpha, xs, x2 are produced directly inside the state buffer
   W.t = reinterpret_cast<double*>(sb + S.t);
@@ -564,9 +593,11 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
   if (rc) return rc;
   rc = run_cov(gp, theta_dev, 1, W, npad, W.kl, st);
   if (rc) return rc;
-  rc = run_factor(gp, 1, W.kl, W.t, info_dev, npad, true, st);
+  e = zero_flags(W, 1, L.nb, st);
+  if (e != cudaSuccess) return fail_cuda("memset flags", e);
+  rc = run_factor(gp, 1, W, info_dev, npad, true, st);
   if (rc) return rc;
-  rc = run_trsv_alpha(gp, 1, W, npad, true, st);
+  rc = run_beta_alpha(gp, 1, W, npad, true, st);
   if (rc) return rc;
   hyp_store_kernel<<<1, 128, 0, st>>>(gp->kd, theta_dev, reinterpret_cast<HypS*>(sb + S.hyp));
   LAUNCH_CHECK("hyp_store_kernel");

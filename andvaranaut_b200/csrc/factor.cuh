@@ -1,0 +1,535 @@
+// K2: batched FP64 Cholesky L = chol(K) and triangular inverse T = L^-1 as ONE persistent dataflow kernel.
+//
+// The factorisation of every sample is cut into 64 x 64 tile tasks of three kinds, for block column / row k:
+//   D(b,k)    A[k,k] -= sum_{m<k} L[k,m] L[k,m]^T ;  L[k,k] = chol(A[k,k]) ;  T[k,k] = L[k,k]^-1 ;  sum log L_ii
+//   P(b,k,i)  L[i,k]  = (A[i,k] - sum_{m<k} L[i,m] L[k,m]^T) T[k,k]^T                          (i > k, left-looking)
+//   R(b,k,j)  T[k,j]  = -T[k,k] sum_{m=j}^{k-1} L[k,m] T[m,j]                                  (j < k, row k of L^-1)
+// Tasks are numbered step-major, the sample index fastest: first D(.,0); then for every step s the tiles
+// P(.,s,s+1), `dgap` more slots of P/R work, the look-ahead diagonal task D(.,s+1) (it only needs P(.,s,s+1), and
+// by the time step s+1 starts it has long finished), the remaining P(.,s,i) by rising i and R(.,s,j) by rising j
+// (longest first).  CTAs are persistent: each takes the next task number from a global ticket counter, waits on
+// per-(sample, block) progress flags for its operands -- slab by slab inside the k loop, so that only the last
+// 64-deep slab of a tile product is on the critical path -- runs the DMMA tile product and publishes its own
+// flag.  A task only ever waits on tasks with smaller numbers, and a number is handed out only to a CTA that is
+// already running, so the waits cannot deadlock; with B * nb tasks per step and ~450 resident CTAs they are
+// rarely taken at all.  There are no launch boundaries, no wave quantisation and no host round trips inside the
+// factorisation (the previous version needed 3 launches per block column).
+//
+// Flags (int32, zeroed by the host before the launch):
+//   lflag[b][i] = number of final 64-wide block columns in block row i of L   (D(b,k) also publishes T[k,k])
+//   tflag[b][j] = number of final block rows in block column j of T, counted as (row index + 1)
+#pragma once
+#include "avn_dev.cuh"
+#include "tile_gemm.cuh"
+
+namespace avn {
+
+using FacKK = TileGemm<64, 64, 16, 32, 32, 3, false, false>;
+using FacKR = TileGemm<64, 64, 16, 32, 32, 3, false, true>;
+constexpr int FAC_THREADS = 128;
+constexpr int FAC_LDS = TILE + SPAD;                                 // 68: conflict-free fragment loads both ways
+constexpr size_t FAC_SMEM_BYTES = (size_t)2 * TILE * FAC_LDS * 8;    // two staged 64 x 64 tiles (>= pipeline buffers)
+static_assert(FacKK::SMEM_BYTES <= FAC_SMEM_BYTES && FacKR::SMEM_BYTES <= FAC_SMEM_BYTES, "pipeline must fit");
+
+#ifdef AVN_FACTOR_PROF
+#define FPROF_DECL long long fp_t0 = clock64(), fp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FPROF(slot)                                   \
+  do {                                                \
+    long long fp_t1 = clock64();                      \
+    fp_acc[slot] += fp_t1 - fp_t0;                    \
+    fp_t0 = fp_t1;                                    \
+  } while (0)
+#define FPROF_FLUSH(p)                                                                       \
+  do {                                                                                       \
+    if (threadIdx.x == 0 && (p))                                                             \
+      for (int q = 0; q < 8; q++) atomicAdd(reinterpret_cast<unsigned long long*>(p) + q, (unsigned long long)fp_acc[q]); \
+  } while (0)
+#else
+#define FPROF_DECL
+#define FPROF(slot)
+#define FPROF_FLUSH(p)
+#endif
+
+struct FactorArgs {
+  double* L;            // [B][npad][npad]  K on entry (lower block triangle), L on exit
+  double* T;            // [B][npad][npad]  T = L^-1 (lower block triangle; diagonal blocks with explicit zeros)
+  double* fpart;        // [B][nb][2]       [.][1] = sum of log L_ii over the block (slot 0 belongs to beta_kernel)
+  int32_t* info;        // [B]              first non-positive pivot (1-based) or 0
+  int32_t* lflag;       // [B][nb]
+  int32_t* tflag;       // [B][nb]
+  int32_t* ctl;         // [0] ticket counter, [1] abort flag (a wait exceeded its bound)
+  int npad, nb, B;
+  int want_inverse;     // 0: skip the R tasks (log-likelihood only)
+  int dgap;             // slots between P(.,s,s+1) and the look-ahead D(.,s+1)
+  long long* prof;      // AVN_FACTOR_PROF builds: 8 cycle counters (ticket, wait, gemm, wait T_kk, epilogue, diag, -, -)
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// thread 0 polls until *flag >= need (bounded: ~1 s, then the abort flag ends every later wait at once)
+__device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t* ctl) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire(flag) < need) {
+      __nanosleep(64);
+      if ((++spins & 1023u) == 0) {
+        if (ld_acquire(ctl + 1) != 0) break;
+        if (spins > (1u << 23)) {
+          atomicExch(ctl + 1, 1);
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence();
+}
+
+// Slab-wise operand wait inside TileGemm::run: k-slab kt belongs to the 64-deep block m = m0 + kt / 4, which
+// needs both progress flags >= m + 1.  `known` caches the smaller flag value seen last, so the flags are only
+// read again (thread 0, then one barrier) when the product runs ahead of what was known to be final.
+struct SlabWaiter {
+  const int32_t* fa;
+  const int32_t* fb;
+  int32_t* ctl;
+  int* s_known;
+  int m0, known;
+  __device__ __forceinline__ void operator()(int kt) {
+    if (kt & 3) return;
+    const int need = m0 + (kt >> 2) + 1;
+    if (need <= known) return;
+    if (threadIdx.x == 0) {
+      unsigned spins = 0;
+      int have;
+      for (;;) {
+        const int va = ld_acquire(fa), vb = ld_acquire(fb);
+        have = va < vb ? va : vb;
+        if (have >= need) break;
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0) {
+          if (ld_acquire(ctl + 1) != 0) { have = 0x7fffffff; break; }
+          if (spins > (1u << 23)) {
+            atomicExch(ctl + 1, 1);
+            have = 0x7fffffff;
+            break;
+          }
+        }
+      }
+      *s_known = have;
+    }
+    __syncthreads();
+    known = *s_known;
+    __threadfence();
+  }
+};
+
+// all threads have written their part of a tile: make it visible, then publish the flag
+__device__ __forceinline__ void publish(int32_t* flag, int value) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release(flag, value);
+}
+__device__ __forceinline__ void publish2(int32_t* f0, int v0, int32_t* f1, int v1) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release(f0, v0);
+    st_release(f1, v1);
+  }
+}
+
+// acc(m,n) += sum_c sA[m][c] * (B_KN ? sB[c][n] : sB[n][c]); 64x64x64 from shared memory, warp tile 32x32
+template <bool B_KN>
+__device__ __forceinline__ void smem_gemm64x(double (&acc)[4][4][2], const double* sA, const double* sB, int wm, int wn,
+                                             int g, int t, int kmax) {
+#pragma unroll 4
+  for (int kk = 0; kk < kmax; kk += 4) {
+    double a[4], bb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = sA[(wm * 32 + i * 8 + g) * FAC_LDS + kk + t];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      bb[j] = B_KN ? sB[(kk + t) * FAC_LDS + wn * 32 + j * 8 + g] : sB[(wn * 32 + j * 8 + g) * FAC_LDS + kk + t];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+  }
+}
+
+// copy a 64 x 64 global tile (row stride ld) into a staged shared tile, bypassing L1 (the data was written by
+// another SM during this launch)
+__device__ __forceinline__ void stage_tile(double* s, const double* __restrict__ g, int64_t ld) {
+  for (int e = threadIdx.x; e < TILE * TILE / 2; e += FAC_THREADS) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(g + (int64_t)r * ld + c));
+    *reinterpret_cast<double2*>(&s[r * FAC_LDS + c]) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64 x 64 diagonal block: Cholesky and triangular inverse, 128 threads, one barrier per column.
+// The block is held in registers as a 16 x 16 grid of 4 x 4 sub-blocks; thread (ty, tx), ty in 0..7, owns the
+// sub-blocks (ty, tx) and (ty + 8, tx).  Column j: its owners have published the (updated, unscaled) column in
+// vec[j & 1]; after the barrier every thread forms 1/sqrt(pivot) itself, the owners scale and keep the column,
+// everyone applies the rank-1 update to the columns right of j and the owners of column j+1 publish it.
+// sA holds A (lower part) on entry and L (zeros above the diagonal) on exit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void diag_chol_inv(double* sA, double* sT, double* vec /*[2][64]*/, double* dinv /*[64]*/,
+                                              double* dval /*[64]*/, int* s_bad, int pivot_base) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double a[2][4][4];
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) a[h][r][c] = sA[(4 * (ty + 8 * h) + r) * FAC_LDS + 4 * tx + c];
+  if (tx == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) vec[4 * (ty + 8 * h) + r] = a[h][r][0];
+  }
+  for (int jb = 0; jb < 16; jb++) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = 4 * jb + jj;
+      double* vcur = vec + (j & 1) * TILE;
+      double* vnxt = vec + ((j + 1) & 1) * TILE;
+      __syncthreads();
+      double piv = vcur[j];
+      if (!(piv > 0.0)) {  // also catches NaN
+        if (tid == 0 && *s_bad == 0) *s_bad = pivot_base + j + 1;
+        piv = 1.0;
+      }
+      const double inv = rsqrt(piv);
+      if (tid == 0) {
+        dinv[j] = inv;
+        dval[j] = piv * inv;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int vty = ty + 8 * h;
+        if (vty < jb || tx > vty) continue;   // rows above the pivot block / strictly upper sub-blocks
+        double lr[4], lc[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) lr[r] = vcur[4 * vty + r] * inv;
+#pragma unroll
+        for (int c = 0; c < 4; c++) lc[c] = vcur[4 * tx + c] * inv;
+        if (tx == jb) {
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const int row = 4 * vty + r;
+            a[h][r][jj] = (row == j) ? piv * inv : (row > j ? lr[r] : a[h][r][jj]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            if (4 * tx + c > j && 4 * vty + r > j) a[h][r][c] = fma(-lr[r], lc[c], a[h][r][c]);
+        // publish column j+1 for the next step
+        if (jj < 3) {
+          if (tx == jb) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) vnxt[4 * vty + r] = a[h][r][jj + 1 > 3 ? 3 : jj + 1];
+          }
+        } else if (tx == jb + 1) {
+#pragma unroll
+          for (int r = 0; r < 4; r++) vnxt[4 * vty + r] = a[h][r][0];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // L to shared memory (zeros above the diagonal)
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int row = 4 * (ty + 8 * h) + r, col = 4 * tx + c;
+        sA[row * FAC_LDS + col] = (col <= row) ? a[h][r][c] : 0.0;
+      }
+  // ---- T = L^-1 by the same right-looking sweep on the rows of the identity: after step j-1 row j of the
+  // working matrix only misses the division by L_jj; its owners scale and publish it, then
+  // R[i,:] -= L[i,j] T[j,:] for the rows below. ----
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) a[h][r][c] = (4 * (ty + 8 * h) + r == 4 * tx + c) ? 1.0 : 0.0;
+  __syncthreads();
+  if (ty == 0) {   // row 0 of T
+    const double inv0 = dinv[0];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double v = (4 * tx + c == 0) ? inv0 : 0.0;
+      a[0][0][c] = v;
+      vec[4 * tx + c] = v;
+    }
+  }
+  for (int jb = 0; jb < 16; jb++) {
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = 4 * jb + jj;
+      const double* vcur = vec + (j & 1) * TILE;
+      double* vnxt = vec + ((j + 1) & 1) * TILE;
+      __syncthreads();
+      const double invn = (j + 1 < TILE) ? dinv[j + 1] : 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int vty = ty + 8 * h;
+        if (vty < jb || tx > vty) continue;
+        double tc[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) tc[c] = vcur[4 * tx + c];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int row = 4 * vty + r;
+          if (row > j) {
+            const double lij = sA[row * FAC_LDS + j];
+#pragma unroll
+            for (int c = 0; c < 4; c++) a[h][r][c] = fma(-lij, tc[c], a[h][r][c]);
+          }
+        }
+        // owners of row j+1: scale by 1/L_{j+1,j+1}, keep and publish
+        const int jn = j + 1;
+        if (jn < TILE && vty == (jn >> 2)) {
+          const int rn = (jj + 1) & 3;
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+            if (r == rn) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                const double v = (4 * tx + c <= jn) ? a[h][r][c] * invn : 0.0;
+                a[h][r][c] = v;
+                vnxt[4 * tx + c] = v;
+              }
+            }
+        }
+      }
+      // sub-blocks right of the diagonal never run the loop body: their share of the published row is zero
+      if (j + 1 < TILE) {
+        const int vt = (j + 1) >> 2;
+        if ((ty == (vt & 7)) && tx > vt) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) vnxt[4 * tx + c] = 0.0;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int row = 4 * (ty + 8 * h) + r, col = 4 * tx + c;
+        sT[row * FAC_LDS + col] = (col <= row) ? a[h][r][c] : 0.0;
+      }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_ticket;
+  __shared__ int s_known;
+  __shared__ int s_bad;
+  __shared__ __align__(16) double s_vec[2 * TILE];
+  __shared__ double s_dinv[TILE], s_dval[TILE];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % 2, wn = warp / 2, gq = lane >> 2, t = lane & 3;
+  const int npad = fa.npad, nb = fa.nb, B = fa.B;
+  const int per_step = B * nb;
+  const int total = per_step * nb;
+  double* sA = smem;
+  double* sB = smem + TILE * FAC_LDS;
+  FPROF_DECL;
+  for (;;) {
+    __syncthreads();  // everyone is done with s_ticket and the staged tiles of the previous task
+    if (tid == 0) s_ticket = atomicAdd(fa.ctl, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    FPROF(0);
+    if (ticket >= total) break;
+    // ticket -> task (see the header comment for the order)
+    int type, k, idx = 0, b;   // type 0: D(b,k)   1: P(b,k,i=idx)   2: R(b,k,j=idx)
+    if (ticket < B) {
+      type = 0; k = 0; b = ticket;
+    } else {
+      const int t2 = ticket - B;
+      const int s = t2 / per_step, rem = t2 - s * per_step;
+      const int q = rem / B;
+      b = rem - q * B;
+      k = s;
+      if (s < nb - 1) {
+        const int dpos = (1 + fa.dgap < nb - 1) ? 1 + fa.dgap : nb - 1;
+        if (q == dpos) {
+          type = 0; k = s + 1;
+        } else {
+          const int r = q < dpos ? q : q - 1;
+          if (r < nb - 1 - s) { type = 1; idx = s + 1 + r; }
+          else { type = 2; idx = r - (nb - 1 - s); }
+        }
+      } else {
+        type = 2; idx = q;
+      }
+    }
+    const int k0 = k * TILE;
+    double* L = fa.L + (int64_t)b * npad * npad;
+    double* T = fa.T + (int64_t)b * npad * npad;
+    int32_t* lflag = fa.lflag + (int64_t)b * nb;
+    int32_t* tflag = fa.tflag + (int64_t)b * nb;
+    if (type == 0) {
+      // ---------------- D(b,k) ----------------
+      FacKK g;
+      g.zero();
+      if (k > 0) {
+        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
+        g.run(smem, L + (int64_t)k0 * npad, npad, 64, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); });
+        FPROF(2);
+      }
+      double* Akk = L + (int64_t)k0 * npad + k0;
+      double* Tkk = T + (int64_t)k0 * npad + k0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(Akk + (int64_t)r * npad + c));
+          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(v.x - g.acc[i][j][0], v.y - g.acc[i][j][1]);
+        }
+      if (tid == 0) s_bad = __ldcg(fa.info + b);
+      __syncthreads();
+      diag_chol_inv(sA, sB, s_vec, s_dinv, s_dval, &s_bad, k0);
+      for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sA[r * FAC_LDS + c]);
+        *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sB[r * FAC_LDS + c]);
+      }
+      if (warp == 0) {   // sum of log L_ii in a fixed order
+        double v = log(s_dval[lane]) + log(s_dval[lane + 32]);
+        v = warp_sum(v);
+        if (lane == 0) {
+          fa.fpart[((int64_t)b * nb + k) * 2 + 1] = v;
+          fa.info[b] = s_bad;
+        }
+      }
+      publish2(lflag + k, k + 1, tflag + k, k + 1);
+      FPROF(5);
+    } else if (type == 1) {
+      // ---------------- P(b,k,i) ----------------
+      const int i = idx, i0 = i * TILE;
+      FacKK g;
+      g.zero();
+      if (k > 0) {
+        SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0};
+        g.run(smem, L + (int64_t)i0 * npad, npad, 64, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); });
+        FPROF(2);
+      }
+      double* Aik = L + (int64_t)i0 * npad + k0;
+#pragma unroll
+      for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(Aik + (int64_t)r * npad + c));
+          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(v.x - g.acc[ii][j][0], v.y - g.acc[ii][j][1]);
+        }
+      FPROF(4);
+      wait_flag(lflag + k, k + 1, fa.ctl);   // T[k,k] is there (also orders the sA writes)
+      FPROF(3);
+      stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
+      __syncthreads();
+      g.zero();
+      smem_gemm64x<false>(g.acc, sA, sB, wm, wn, gq, t, wn == 0 ? 32 : 64);   // X T_kk^T, T_kk lower triangular
+#pragma unroll
+      for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+          *reinterpret_cast<double2*>(Aik + (int64_t)r * npad + c) = make_double2(g.acc[ii][j][0], g.acc[ii][j][1]);
+        }
+      publish(lflag + i, k + 1);
+      FPROF(4);
+    } else {
+      // ---------------- R(b,k,j) ----------------
+      if (!fa.want_inverse) continue;
+      const int j = idx, j0 = j * TILE;
+      FacKR g;
+      g.zero();
+      SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0};
+      g.run(smem, L + (int64_t)k0 * npad + j0, npad, 64, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
+            [&](int kt) { w(kt); });
+      FPROF(2);
+#pragma unroll
+      for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + jj * 8 + 2 * t;
+          *reinterpret_cast<double2*>(&sB[r * FAC_LDS + c]) = make_double2(g.acc[ii][jj][0], g.acc[ii][jj][1]);
+        }
+      FPROF(4);
+      wait_flag(lflag + k, k + 1, fa.ctl);
+      FPROF(3);
+      stage_tile(sA, T + (int64_t)k0 * npad + k0, npad);
+      __syncthreads();
+      g.zero();
+      smem_gemm64x<true>(g.acc, sA, sB, wm, wn, gq, t, wm == 0 ? 32 : 64);    // T_kk S, T_kk lower triangular
+      double* Tkj = T + (int64_t)k0 * npad + j0;
+#pragma unroll
+      for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + jj * 8 + 2 * t;
+          *reinterpret_cast<double2*>(Tkj + (int64_t)r * npad + c) = make_double2(-g.acc[ii][jj][0], -g.acc[ii][jj][1]);
+        }
+      publish(tflag + j, k + 1);
+      FPROF(4);
+    }
+  }
+  FPROF_FLUSH(fa.prof);
+}
+
+// beta = T z  (= L^-1 z), block row k per CTA, and the block's share of beta^T beta.  grid (nb, B), 256 threads.
+__global__ void __launch_bounds__(256) beta_kernel(const double* __restrict__ Tall, const double* __restrict__ zall,
+                                                   int npad, double* __restrict__ beta_all, double* __restrict__ fpart) {
+  __shared__ double red[TILE];
+  const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x, nb = gridDim.x;
+  const int row = tid >> 2, part = tid & 3;
+  const double* Tr = Tall + (int64_t)b * npad * npad + (int64_t)(k * TILE + row) * npad;
+  const double* z = zall + (int64_t)b * npad;
+  double s = 0.0;
+  for (int c = part * 4; c < (k + 1) * TILE; c += 16) {
+    const double2 a0 = *reinterpret_cast<const double2*>(Tr + c);
+    const double2 a1 = *reinterpret_cast<const double2*>(Tr + c + 2);
+    const double2 z0 = *reinterpret_cast<const double2*>(z + c);
+    const double2 z1 = *reinterpret_cast<const double2*>(z + c + 2);
+    s += (a0.x * z0.x + a0.y * z0.y) + (a1.x * z1.x + a1.y * z1.y);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (part == 0) {
+    beta_all[(int64_t)b * npad + k * TILE + row] = s;
+    red[row] = s * s;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double q = red[tid] + red[tid + 32];
+    q = warp_sum(q);
+    if (tid == 0) fpart[((int64_t)b * nb + k) * 2] = q;
+  }
+}
+
+}  // namespace avn

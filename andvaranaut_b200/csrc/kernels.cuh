@@ -7,6 +7,7 @@
 #include "avn_dev.cuh"
 #include "tile_gemm.cuh"
 #include "warp.cuh"
+#include "factor.cuh"
 
 namespace avn {
 
@@ -17,13 +18,17 @@ struct WsPtrs {
   double* x2;      // [B][nkern][npad]        row norms of xs (NumPy summation order)
   double* z;       // [B][npad]               converted outputs
   double* dz;      // [B][npad][MAXWP]        d z / d output-warp params
-  double* wstat;   // [B][16]                 0: sum log g'; 1..8: its param derivatives; 9: quad; 10: logdet
+  double* wstat;   // [B][16]                 0: sum log g'; 1..8: its param derivatives
   double* kl;      // [B][npad][npad]         K then L
   double* t;       // [B][npad][npad]         T = L^-1
   double* beta;    // [B][npad]
   double* alpha;   // [B][npad]
   double* gpart;   // [B][ntiles][MAXACC]     per-tile partial sums of the gradient contraction
   double* gxpart;  // [B][nb][npad][d]        per-source-tile partial sums of d ll / d warped input
+  double* fpart;   // [B][nb][2]              per block row: beta_k^T beta_k, sum log diag(L_kk)
+  int32_t* lflag;  // [B][nb]                 progress flags of the factor kernel (factor.cuh)
+  int32_t* tflag;  // [B][nb]
+  int32_t* ctl;    // [8]                     ticket counter, abort flag
 };
 
 constexpr int WSTAT = 16;
@@ -170,325 +175,7 @@ __global__ void __launch_bounds__(256) cov_kernel(KernDesc kd, int N, int npad, 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2: blocked left-looking Cholesky, one launch triple per 64-wide block column k:
-//   potrf_update : A[i,k] -= sum_{j<k} L[i,j] L[k,j]^T          (DMMA, i >= k)
-//   potrf_diag   : L[k,k] = chol(A[k,k]);  T[k,k] = L[k,k]^-1    (shared memory, one CTA per sample)
-//   potrf_panel  : L[i,k] = A[i,k] T[k,k]^T                      (DMMA, i > k)
-// ------------------------------------------------------------------------------------------------
-template <int BM>
-struct PotrfCfg {
-  using G = TileGemm<BM, 64, 16, 32, 32, 3, false, false>;  // 3 stages: 92 KB -> 2 CTAs/SM
-};
-
-template <int BM>
-__global__ void __launch_bounds__(PotrfCfg<BM>::G::NTHREADS) potrf_update_kernel(double* __restrict__ Lall, int npad,
-                                                                                  int kblk) {
-  using G = typename PotrfCfg<BM>::G;
-  extern __shared__ double smem[];
-  const int b = blockIdx.y;
-  double* L = Lall + (int64_t)b * npad * npad;
-  const int r0 = kblk * TILE + blockIdx.x * BM;
-  const int rows = min(BM, npad - r0);
-  G g;
-  g.zero();
-  g.run(smem, L + (int64_t)r0 * npad, npad, rows, L + (int64_t)kblk * TILE * npad, npad, 64, kblk * TILE);
-  double* C = L + (int64_t)r0 * npad + kblk * TILE;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int i = 0; i < G::MI; i++)
-#pragma unroll
-    for (int j = 0; j < G::NI; j++) {
-      int r = wm * G::WM + i * 8 + gq, c = wn * G::WN + j * 8 + 2 * t;
-      if (r < rows) {
-        double2* p = reinterpret_cast<double2*>(C + (int64_t)r * npad + c);
-        double2 v = *p;
-        v.x -= g.acc[i][j][0];
-        v.y -= g.acc[i][j][1];
-        *p = v;
-      }
-    }
-}
-
-template <int BM>
-__global__ void __launch_bounds__(PotrfCfg<BM>::G::NTHREADS) potrf_panel_kernel(double* __restrict__ Lall,
-                                                                                 const double* __restrict__ Tall,
-                                                                                 int npad, int kblk) {
-  using G = typename PotrfCfg<BM>::G;
-  extern __shared__ double smem[];
-  const int b = blockIdx.y;
-  double* L = Lall + (int64_t)b * npad * npad;
-  const double* T = Tall + (int64_t)b * npad * npad;
-  const int r0 = (kblk + 1) * TILE + blockIdx.x * BM;
-  const int rows = min(BM, npad - r0);
-  G g;
-  g.zero();
-  double* A = L + (int64_t)r0 * npad + kblk * TILE;
-  g.run(smem, A, npad, rows, T + (int64_t)kblk * TILE * npad + kblk * TILE, npad, 64, TILE);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int i = 0; i < G::MI; i++)
-#pragma unroll
-    for (int j = 0; j < G::NI; j++) {
-      int r = wm * G::WM + i * 8 + gq, c = wn * G::WN + j * 8 + 2 * t;
-      if (r < rows)
-        *reinterpret_cast<double2*>(A + (int64_t)r * npad + c) = make_double2(g.acc[i][j][0], g.acc[i][j][1]);
-    }
-}
-
-// diagonal block: unblocked Cholesky + triangular inverse.  grid (B), 256 threads.
-// Thread (ty, tx) of a 16 x 16 grid keeps the 4 x 4 sub-block (rows 4ty.., cols 4tx..) in registers; the 64 column
-// steps are fully unrolled (static register indexing, ~40 instructions each so the code stays inside the
-// instruction cache).  Step j: the pivot owner publishes 1/L_jj, the owners of column j scale it and publish it,
-// every thread applies the rank-1 update to its sub-block.  The inverse T = L^-1 is the same right-looking sweep
-// on the rows of the identity (row j of T final after step j, then R[i,:] -= L[i,j] T[j,:]).
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Lall, double* __restrict__ Tall,
-                                                         int npad, int kblk, int32_t* __restrict__ info) {
-  constexpr int LD = TILE + 2;
-  __shared__ __align__(16) double Ls[TILE * LD];
-  __shared__ __align__(16) double vec[TILE];
-  __shared__ double invd[TILE];
-  __shared__ double pivinv;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  double* Lkk = Lall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
-  double* Tkk = Tall + (int64_t)b * npad * npad + (int64_t)kblk * TILE * npad + kblk * TILE;
-  double a[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const double2* src = reinterpret_cast<const double2*>(Lkk + (int64_t)(4 * ty + r) * npad + 4 * tx);
-    const double2 v0 = src[0], v1 = src[1];
-    a[r][0] = v0.x; a[r][1] = v0.y; a[r][2] = v1.x; a[r][3] = v1.y;
-  }
-  // ---- Cholesky ----
-#pragma unroll
-  for (int j = 0; j < TILE; j++) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int jb = j >> 2, jj = j & 3;
-    if (ty == jb && tx == jb) {
-      double dj = a[jj][jj];
-      if (!(dj > 0.0)) {  // also catches NaN
-        if (info[b] == 0) info[b] = kblk * TILE + j + 1;
-        dj = 1.0;
-      }
-      // one reciprocal square root instead of a sqrt followed by a division on the critical path
-      const double inv = rsqrt(dj);
-      a[jj][jj] = dj * inv;
-      pivinv = inv;
-      invd[j] = inv;
-    }
-    __syncthreads();
-    if (tx == jb && ty >= jb) {
-      const double inv = pivinv;
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int row = 4 * ty + r;
-        double l = 0.0;
-        if (row > j) {
-          l = a[r][jj] * inv;
-          a[r][jj] = l;
-        }
-        vec[row] = l;
-      }
-    } else if (tx == jb && ty < jb) {
-#pragma unroll
-      for (int r = 0; r < 4; r++) vec[4 * ty + r] = 0.0;
-    }
-    __syncthreads();
-    if (tx <= ty && ty >= jb) {
-      const double2 r0 = *reinterpret_cast<const double2*>(&vec[4 * ty]), r1 = *reinterpret_cast<const double2*>(&vec[4 * ty + 2]);
-      const double2 c0 = *reinterpret_cast<const double2*>(&vec[4 * tx]), c1 = *reinterpret_cast<const double2*>(&vec[4 * tx + 2]);
-      const double cr[4] = {r0.x, r0.y, r1.x, r1.y}, cc[4] = {c0.x, c0.y, c1.x, c1.y};
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-          if (4 * tx + c > j) a[r][c] = fma(-cr[r], cc[c], a[r][c]);   // columns <= j are final
-    }
-  }
-  // L (lower part) to shared memory and to global
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) Ls[(4 * ty + r) * LD + 4 * tx + c] = (4 * tx + c <= 4 * ty + r) ? a[r][c] : 0.0;
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    double2* dst = reinterpret_cast<double2*>(Lkk + (int64_t)(4 * ty + r) * npad + 4 * tx);
-    const double* srow = &Ls[(4 * ty + r) * LD + 4 * tx];
-    dst[0] = make_double2(srow[0], srow[1]);
-    dst[1] = make_double2(srow[2], srow[3]);
-  }
-  // ---- T = L^-1: start from the identity ----
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) a[r][c] = (4 * ty + r == 4 * tx + c) ? 1.0 : 0.0;
-#pragma unroll
-  for (int j = 0; j < TILE; j++) {
-    const int jb = j >> 2, jj = j & 3;
-    // row j of T is final once divided by L_jj; publish it (zero right of the diagonal)
-    if (ty == jb) {
-      const double inv = invd[j];
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const double v = (4 * tx + c <= j) ? a[jj][c] * inv : 0.0;
-        a[jj][c] = v;
-        vec[4 * tx + c] = v;
-      }
-    }
-    __syncthreads();
-    if (tx <= ty && ty >= jb) {
-      const double2 c0 = *reinterpret_cast<const double2*>(&vec[4 * tx]), c1 = *reinterpret_cast<const double2*>(&vec[4 * tx + 2]);
-      const double cc[4] = {c0.x, c0.y, c1.x, c1.y};
-#pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const int row = 4 * ty + r;
-        const double lij = (row > j) ? Ls[row * LD + j] : 0.0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) a[r][c] = fma(-lij, cc[c], a[r][c]);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    double2* dst = reinterpret_cast<double2*>(Tkk + (int64_t)(4 * ty + r) * npad + 4 * tx);
-    double o[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) o[c] = (4 * tx + c <= 4 * ty + r) ? a[r][c] : 0.0;
-    dst[0] = make_double2(o[0], o[1]);
-    dst[1] = make_double2(o[2], o[3]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// beta = L^-1 z by blocked forward substitution (diagonal blocks through T[k,k]), plus the two
-// scalars of the log-likelihood:  quad = beta^T beta,  logdet = sum log L_ii.   grid (B), 256 threads.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ Lall, const double* __restrict__ Tall,
-                                                   const double* __restrict__ zall, int npad,
-                                                   double* __restrict__ beta_all, double* __restrict__ wstat) {
-  extern __shared__ double sbeta[];  // npad + 64 + 32
-  double* rt = sbeta + npad;
-  double* red = rt + TILE;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const double* L = Lall + (int64_t)b * npad * npad;
-  const double* T = Tall + (int64_t)b * npad * npad;
-  const double* z = zall + (int64_t)b * npad;
-  const int nb = npad / TILE;
-  const int row = tid >> 2, part = tid & 3;
-  double logdet = 0.0;
-  for (int k = 0; k < nb; k++) {
-    const double* Lr = L + (int64_t)(k * TILE + row) * npad;
-    double s = 0.0;
-    for (int j = part * 4; j < k * TILE; j += 16) {
-      const double2 a0 = *reinterpret_cast<const double2*>(Lr + j);
-      const double2 a1 = *reinterpret_cast<const double2*>(Lr + j + 2);
-      s += a0.x * sbeta[j] + a0.y * sbeta[j + 1] + a1.x * sbeta[j + 2] + a1.y * sbeta[j + 3];
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (part == 0) rt[row] = z[k * TILE + row] - s;
-    __syncthreads();
-    if (tid < TILE) {
-      const double* Tr = T + (int64_t)(k * TILE + tid) * npad + k * TILE;
-      double acc = 0.0;
-      for (int c = 0; c <= tid; c++) acc += Tr[c] * rt[c];
-      sbeta[k * TILE + tid] = acc;
-      logdet += log(L[(int64_t)(k * TILE + tid) * npad + k * TILE + tid]);
-    }
-    __syncthreads();
-  }
-  double q = 0.0;
-  for (int n = tid; n < npad; n += 256) {
-    double v = sbeta[n];
-    beta_all[(int64_t)b * npad + n] = v;
-    q += v * v;
-  }
-  double quad = block_sum(q, red);
-  double ld = block_sum(logdet, red);
-  if (tid == 0) {
-    wstat[(int64_t)b * WSTAT + 9] = quad;
-    wstat[(int64_t)b * WSTAT + 10] = ld;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2b: T = L^-1, block row i:  T[i,j] = -T[i,i] * sum_{k=j}^{i-1} L[i,k] T[k,j]   (j < i)
-// grid (i, B): one 64x64 output tile per CTA, 128 threads.
-// ------------------------------------------------------------------------------------------------
-using TrtriG = TileGemm<64, 64, 16, 32, 32, 3, false, true>;  // 3 stages: 57 KB -> 3 CTAs/SM
-
-template <int LDA, int LDB>
-__device__ __forceinline__ void smem_gemm64(double (&acc)[4][4][2], const double* sA,
-                                            const double* sB, int wm, int wn, int g, int t) {
-  // acc(m,n) += sum_k sA[m][k] * sB[k][n], 64x64x64, warp tile 32x32
-#pragma unroll 4
-  for (int kk = 0; kk < 64; kk += 4) {
-    double a[4], bb[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) a[i] = sA[(wm * 32 + i * 8 + g) * LDA + kk + t];
-#pragma unroll
-    for (int j = 0; j < 4; j++) bb[j] = sB[(kk + t) * LDB + wn * 32 + j * 8 + g];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
-  }
-}
-
-__global__ void __launch_bounds__(TrtriG::NTHREADS) trtri_row_kernel(const double* __restrict__ Lall,
-                                                                     double* __restrict__ Tall, int npad, int iblk) {
-  using G = TrtriG;
-  constexpr int LDS = TILE + SPAD;
-  extern __shared__ double smem[];
-  const int b = blockIdx.y, jblk = blockIdx.x;
-  const double* L = Lall + (int64_t)b * npad * npad;
-  double* T = Tall + (int64_t)b * npad * npad;
-  const int i0 = iblk * TILE, j0 = jblk * TILE;
-  G g;
-  g.zero();
-  g.run(smem, L + (int64_t)i0 * npad + j0, npad, 64, T + (int64_t)j0 * npad + j0, npad, 64, i0 - j0);
-  // S -> smem as [k][n]; T[i,i] -> smem as [m][k]
-  double* sS = smem;
-  double* sT = smem + TILE * LDS;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int i = 0; i < G::MI; i++)
-#pragma unroll
-    for (int j = 0; j < G::NI; j++) {
-      int r = wm * G::WM + i * 8 + gq, c = wn * G::WN + j * 8 + 2 * t;
-      sS[r * LDS + c] = g.acc[i][j][0];
-      sS[r * LDS + c + 1] = g.acc[i][j][1];
-    }
-  const double* Tii = T + (int64_t)i0 * npad + i0;
-  for (int e = tid; e < TILE * TILE / 2; e += G::NTHREADS) {
-    int r = e / (TILE / 2), c = (e % (TILE / 2)) * 2;
-    double2 v = *reinterpret_cast<const double2*>(Tii + (int64_t)r * npad + c);
-    sT[r * LDS + c] = v.x;
-    sT[r * LDS + c + 1] = v.y;
-  }
-  __syncthreads();
-  double acc2[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc2[i][j][0] = acc2[i][j][1] = 0.0;
-  smem_gemm64<LDS, LDS>(acc2, sT, sS, wm, wn, gq, t);
-  double* out = T + (int64_t)i0 * npad + j0;
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-      *reinterpret_cast<double2*>(out + (int64_t)r * npad + c) = make_double2(-acc2[i][j][0], -acc2[i][j][1]);
-    }
-}
+// K2 (Cholesky + triangular inverse + beta) lives in factor.cuh.
 
 // alpha = T^T beta.  grid (nb, B), 256 threads.
 __global__ void __launch_bounds__(256) alpha_kernel(const double* __restrict__ Tall, const double* __restrict__ beta_all,
@@ -724,7 +411,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   const bool bad = info[b] != 0;
   if (tid == 0) {
     const double norm = -0.5 * N * 1.8378770664093454835606594728112;  // log(2 pi)
-    double v = (norm - 0.5 * wst[9]) - wst[10] + wst[0];
+    const int nbk = npad / TILE;
+    const double* fp = ws.fpart + (int64_t)b * nbk * 2;
+    double quad = 0.0, logdet = 0.0;   // fixed order: deterministic
+    for (int k = 0; k < nbk; k++) {
+      quad += fp[2 * k];
+      logdet += fp[2 * k + 1];
+    }
+    double v = (norm - 0.5 * quad) - logdet + wst[0];
     ll[b] = bad ? -INFINITY : v;
   }
   if (!want_grad) return;

@@ -117,6 +117,14 @@ struct TileGemm {
   // Apt/Bpt point at (row 0, k = 0) of the respective tiles.  All threads of the CTA must call.
   __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda,
                                       int a_rows, const double* Bpt, int64_t ldb, int b_rows, int klen) {
+    run(smem, Apt, lda, a_rows, Bpt, ldb, b_rows, klen, [](int) {});
+  }
+
+  // As above; pre_issue(kt) is called by every thread (uniformly) before the loads of k-slab kt are issued,
+  // so that a dataflow kernel can wait for operands that other CTAs are still producing.
+  template <typename PreIssue>
+  __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda, int a_rows, const double* Bpt,
+                                      int64_t ldb, int b_rows, int klen, PreIssue pre_issue) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
@@ -131,14 +139,20 @@ struct TileGemm {
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-      if (s < KT) issue(s);
+      if (s < KT) {
+        pre_issue(s);
+        issue(s);
+      }
       cp_async_commit();
     }
     for (int kt = 0; kt < KT; kt++) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       int nk = kt + STAGES - 1;
-      if (nk < KT) issue(nk);
+      if (nk < KT) {
+        pre_issue(nk);
+        issue(nk);
+      }
       cp_async_commit();
       const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
       compute_stage(sA, sA + TA::SIZE, wm, wn, g, t);

@@ -212,7 +212,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='hyperparameter samples per GPU per step (c2)')
-    ap.add_argument('--streams', type=int, default=4, help='concurrent sample groups inside one call')
+    ap.add_argument('--streams', type=int, default=1, help='concurrent sample groups inside one call')
     ap.add_argument('--no-extra', action='store_true', help='skip the c3 / c4 side measurements')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
     args = ap.parse_args()

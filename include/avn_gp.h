@@ -81,7 +81,7 @@ typedef struct {
 /* byte offsets of the named buffers inside a loglik workspace (for tests and profiling) */
 typedef struct {
   int64_t npad, nb;
-  int64_t xw, dxw, xs, x2, z, dz, wstat, kl, t, beta, alpha, gpart, gxpart, total;
+  int64_t xw, dxw, xs, x2, z, dz, wstat, kl, t, beta, alpha, gpart, gxpart, fpart, fflags, total;
 } avn_ws_layout;
 
 /* Gauss-Hermite reversion / expected improvement, gpmcmc.py:545-569 */

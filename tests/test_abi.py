@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.WarpStage) == 40
     assert C.sizeof(_lib.WarpProg) == 8 + 6 * 40
     assert C.sizeof(_lib.ModelDesc) == 48 + 8 + 17 * 248
-    assert C.sizeof(_lib.WsLayout) == 16 * 8
+    assert C.sizeof(_lib.WsLayout) == 18 * 8
 
 
 def test_create_and_parameter_layout_without_gpu():
