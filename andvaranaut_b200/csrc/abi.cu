@@ -249,8 +249,11 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
 // conversions + scaled inputs for B samples
 static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st) {
   Phase ph(gp, AVN_PH_WARP, st);
-  warp_kernel<<<(unsigned)B, 256, 0, st>>>(gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W);
+  warp_kernel<<<dim3((unsigned)gp->kd.d + 1, (unsigned)B), 256, 0, st>>>(gp->kd, gp->progs, gp->X, gp->y, (int)gp->N,
+                                                                       (int)npad, theta, W);
   LAUNCH_CHECK("warp_kernel");
+  scale_kernel<<<dim3((unsigned)((npad + 255) / 256), (unsigned)B), 256, 0, st>>>(gp->kd, (int)npad, theta, W);
+  LAUNCH_CHECK("scale_kernel");
   return 0;
 }
 
@@ -462,6 +465,10 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
     LAUNCH_CHECK("kinv_grad_kernel");
   }
   Phase phf(gp, AVN_PH_FINALIZE, st);
+  if (want_grad && kd.n_iw > 0) {
+    gx_reduce_kernel<<<dim3((unsigned)((npad * kd.d + 255) / 256), (unsigned)Bg), 256, 0, st>>>((int)npad, kd.d, W.gxpart);
+    LAUNCH_CHECK("gx_reduce_kernel");
+  }
   finalize_kernel<<<(unsigned)Bg, 256, 0, st>>>(kd, gp->progs, (int)gp->N, (int)npad, (int)ntiles, want_grad ? 1 : 0,
                                                 theta, W, info, ll, grad);
   LAUNCH_CHECK("finalize_kernel");

@@ -34,28 +34,28 @@ struct WsPtrs {
 constexpr int WSTAT = 16;
 
 // ------------------------------------------------------------------------------------------------
-// K0: conversions.  One CTA per hyperparameter sample.
+// K0: conversions.  grid (d + 1, B): CTA m < d converts input column m, CTA d converts the outputs.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs, const double* __restrict__ X,
                                                    const double* __restrict__ y, int N, int npad,
                                                    const double* __restrict__ theta, WsPtrs ws) {
   __shared__ double sh[128];
-  __shared__ HypS hyp;
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int b = blockIdx.y, m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const double* th = theta + (int64_t)b * kd.P;
-  load_hyp(hyp, kd, th);
-  double* xw = ws.xw + (int64_t)b * npad * kd.d;
-  for (int e = tid; e < npad * kd.d; e += nt) xw[e] = (e / kd.d < N) ? X[e] : 0.0;
-  __syncthreads();
-  int poff = 0;
-  for (int m = 0; m < kd.d; m++) {
+  if (m < kd.d) {
+    double* xw = ws.xw + (int64_t)b * npad * kd.d + m;
+    for (int n = tid; n < npad; n += nt) xw[(int64_t)n * kd.d] = (n < N) ? X[(int64_t)n * kd.d + m] : 0.0;
     const avn_warp_prog& pr = progs.xw[m];
     if (pr.nstages > 0) {
+      int poff = 0;
+      for (int q = 0; q < m; q++)
+        if (progs.xw[q].nstages > 0) poff += progs.xw[q].nparams;
+      __syncthreads();
       double dummy = 0, ddummy[MAXWP];
       double* dual = ws.dxw + ((int64_t)b * npad * kd.d + m) * MAXWP;
-      run_warp_column(pr, th + kd.off_iw + poff, N, xw + m, kd.d, dual, (int64_t)kd.d * MAXWP, 0, dummy, ddummy, sh);
-      poff += pr.nparams;
+      run_warp_column(pr, th + kd.off_iw + poff, N, xw, kd.d, dual, (int64_t)kd.d * MAXWP, 0, dummy, ddummy, sh);
     }
+    return;
   }
   double* z = ws.z + (int64_t)b * npad;
   for (int n = tid; n < npad; n += nt) z[n] = (n < N) ? y[n] : 0.0;
@@ -74,14 +74,27 @@ __global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs,
   } else if (tid == 0) {
     wst[0] = 0.0;
   }
+}
+
+// scaled copies and row norms per kernel (X * (1/ls); sum(square(.), 1)).  grid (npad / 256, B), one row per thread.
+__global__ void __launch_bounds__(256) scale_kernel(KernDesc kd, int npad, const double* __restrict__ theta, WsPtrs ws) {
+  __shared__ double invl[MAXK][MAXD];
+  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+  const double* th = theta + (int64_t)b * kd.P;
+  for (int i = threadIdx.x; i < kd.nkern * kd.d; i += 256) invl[i / kd.d][i % kd.d] = 1.0 / th[kd.off_l + i];
   __syncthreads();
-  // scaled copies and row norms per kernel (X * (1/ls); sum(square(.), 1))
+  if (n >= npad) return;
+  const double* xw = ws.xw + ((int64_t)b * npad + n) * kd.d;
+  double xr[MAXD];
+  for (int mm = 0; mm < kd.d; mm++) xr[mm] = xw[mm];
   for (int k = 0; k < kd.nkern; k++) {
-    double* xs = ws.xs + ((int64_t)b * kd.nkern + k) * npad * kd.d;
-    double* x2 = ws.x2 + ((int64_t)b * kd.nkern + k) * npad;
-    for (int e = tid; e < npad * kd.d; e += nt) xs[e] = __dmul_rn(xw[e], hyp.invl[k][e % kd.d]);
-    __syncthreads();
-    for (int n = tid; n < npad; n += nt) x2[n] = sumsq_numpy_order(xs + (int64_t)n * kd.d, kd.d);
+    double* xs = ws.xs + (((int64_t)b * kd.nkern + k) * npad + n) * kd.d;
+    double tmp[MAXD];
+    for (int mm = 0; mm < kd.d; mm++) {
+      tmp[mm] = __dmul_rn(xr[mm], invl[k][mm]);
+      xs[mm] = tmp[mm];
+    }
+    ws.x2[((int64_t)b * kd.nkern + k) * npad + n] = sumsq_numpy_order(tmp, kd.d);
   }
 }
 
@@ -397,6 +410,17 @@ __global__ void __launch_bounds__(KinvG::NTHREADS) kinv_grad_kernel(KernDesc kd,
   }
 }
 
+// d ll / d warped input: sum of the per-source-tile partials (fixed order) into slab 0.  grid (npad*d/256, B).
+__global__ void __launch_bounds__(256) gx_reduce_kernel(int npad, int d, double* __restrict__ gxpart) {
+  const int nb = npad / TILE;
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x, slab = (int64_t)npad * d;
+  if (e >= slab) return;
+  double* G = gxpart + (int64_t)blockIdx.y * nb * slab;
+  double gsum = 0.0;
+  for (int s = 0; s < nb; s++) gsum += G[(int64_t)s * slab + e];
+  G[e] = gsum;
+}
+
 // ------------------------------------------------------------------------------------------------
 // finalisation: ll and gradient assembly.  grid (B), 256 threads.
 // ------------------------------------------------------------------------------------------------
@@ -448,14 +472,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   // pair: lanes stride over n, one shuffle reduction, no block-level barrier.
   if (kd.n_iw > 0) {
     const int nb = npad / TILE;
-    // G[n][m] = sum over source tiles, reduced once into slab 0
-    double* G = ws.gxpart + (int64_t)b * nb * npad * d;
-    for (int e = tid; e < N * d; e += 256) {
-      double gsum = 0.0;
-      for (int s = 0; s < nb; s++) gsum += G[(int64_t)s * npad * d + e];
-      G[e] = gsum;
-    }
-    __syncthreads();
+    // G[n][m] = sum over source tiles, already reduced into slab 0 by gx_reduce_kernel
+    const double* G = ws.gxpart + (int64_t)b * nb * npad * d;
     int poff = 0;
     for (int m = 0; m < d; m++) {
       const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;

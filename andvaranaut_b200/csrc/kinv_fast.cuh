@@ -63,7 +63,7 @@ struct KinvFastLayout {
 using KinvG2 = TileGemm<64, 64, 16, 32, 32, 4, true, true>;
 
 template <int KIND, bool WITH_GX>
-__global__ void __launch_bounds__(KinvG2::NTHREADS) kinv_grad_fast_kernel(
+__global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
     KernDesc kd, int N, int npad, const double* __restrict__ theta, const double* __restrict__ Tall,
     const double* __restrict__ alpha_all, const double* __restrict__ xw_all, const double* __restrict__ xs_all,
     const double* __restrict__ x2_all, double* __restrict__ gpart, double* __restrict__ gxpart) {
