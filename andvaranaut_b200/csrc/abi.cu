@@ -302,7 +302,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   FactorArgs fa;
   fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info;
   fa.lflag = W.lflag; fa.tflag = W.tflag; fa.ctl = W.ctl;
-  fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.want_inverse = want_inverse ? 1 : 0;
+  fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.n = (int)gp->N; fa.want_inverse = want_inverse ? 1 : 0;
   fa.dgap = (int)((2 * (int64_t)grid + B - 1) / B);
   fa.prof = nullptr;
 #ifdef AVN_FACTOR_PROF

@@ -24,12 +24,19 @@
 
 namespace avn {
 
-using FacKK = TileGemm<64, 64, 16, 32, 32, 3, false, false>;
-using FacKR = TileGemm<64, 64, 16, 32, 32, 3, false, true>;
+#ifndef AVN_FAC_BK
+#define AVN_FAC_BK 16
+#define AVN_FAC_STAGES 3
+#endif
+constexpr int FAC_BK = AVN_FAC_BK, FAC_STAGES = AVN_FAC_STAGES;
+constexpr int FAC_SPB = TILE / FAC_BK;   // pipeline stages per 64-deep block
+using FacKK = TileGemm<64, 64, FAC_BK, 32, 32, FAC_STAGES, false, false>;
+using FacKR = TileGemm<64, 64, FAC_BK, 32, 32, FAC_STAGES, false, true>;
 constexpr int FAC_THREADS = 128;
 constexpr int FAC_LDS = TILE + SPAD;                                 // 68: conflict-free fragment loads both ways
-constexpr size_t FAC_SMEM_BYTES = (size_t)2 * TILE * FAC_LDS * 8;    // two staged 64 x 64 tiles (>= pipeline buffers)
-static_assert(FacKK::SMEM_BYTES <= FAC_SMEM_BYTES && FacKR::SMEM_BYTES <= FAC_SMEM_BYTES, "pipeline must fit");
+constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
+// two staged 64 x 64 tiles for the epilogues alias the pipeline buffers
+constexpr size_t FAC_SMEM_BYTES = cmax((size_t)2 * TILE * FAC_LDS * 8, cmax(FacKK::SMEM_BYTES, FacKR::SMEM_BYTES));
 
 #ifdef AVN_FACTOR_PROF
 #define FPROF_DECL long long fp_t0 = clock64(), fp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
@@ -59,6 +66,7 @@ struct FactorArgs {
   int32_t* tflag;       // [B][nb]
   int32_t* ctl;         // [0] ticket counter, [1] abort flag (a wait exceeded its bound)
   int npad, nb, B;
+  int n;                // valid rows (N <= npad): tiles of the last block row skip their padding fragments
   int want_inverse;     // 0: skip the R tasks (log-likelihood only)
   int dgap;             // slots between P(.,s,s+1) and the look-ahead D(.,s+1)
   long long* prof;      // AVN_FACTOR_PROF builds: 8 cycle counters (ticket, wait, gemm, wait T_kk, epilogue, diag, -, -)
@@ -92,7 +100,7 @@ __device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t
   __threadfence();
 }
 
-// Slab-wise operand wait inside TileGemm::run: k-slab kt belongs to the 64-deep block m = m0 + kt / 4, which
+// Slab-wise operand wait inside TileGemm::run: k-slab kt belongs to the 64-deep block m = m0 + kt / FAC_SPB, which
 // needs both progress flags >= m + 1.  `known` caches the smaller flag value seen last, so the flags are only
 // read again (thread 0, then one barrier) when the product runs ahead of what was known to be final.
 struct SlabWaiter {
@@ -102,8 +110,8 @@ struct SlabWaiter {
   int* s_known;
   int m0, known;
   __device__ __forceinline__ void operator()(int kt) {
-    if (kt & 3) return;
-    const int need = m0 + (kt >> 2) + 1;
+    if (kt % FAC_SPB) return;
+    const int need = m0 + kt / FAC_SPB + 1;
     if (need <= known) return;
     if (threadIdx.x == 0) {
       unsigned spins = 0;
@@ -391,13 +399,14 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
     double* T = fa.T + (int64_t)b * npad * npad;
     int32_t* lflag = fa.lflag + (int64_t)b * nb;
     int32_t* tflag = fa.tflag + (int64_t)b * nb;
+    const int rows_k = min(TILE, fa.n - k0);   // valid rows of block row k
     if (type == 0) {
       // ---------------- D(b,k) ----------------
       FacKK g;
       g.zero();
       if (k > 0) {
         SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
-        g.run(smem, L + (int64_t)k0 * npad, npad, 64, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); });
+        g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); });
         FPROF(2);
       }
       double* Akk = L + (int64_t)k0 * npad + k0;
@@ -435,7 +444,8 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       g.zero();
       if (k > 0) {
         SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0};
-        g.run(smem, L + (int64_t)i0 * npad, npad, 64, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); });
+        g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
+              [&](int kt) { w(kt); });
         FPROF(2);
       }
       double* Aik = L + (int64_t)i0 * npad + k0;
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       FacKR g;
       g.zero();
       SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0};
-      g.run(smem, L + (int64_t)k0 * npad + j0, npad, 64, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
+      g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
             [&](int kt) { w(kt); });
       FPROF(2);
 #pragma unroll

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(KinvG::NTHREADS) kinv_grad_kernel(KernDesc kd,
   load_hyp(hyp, kd, theta + (int64_t)b * kd.P);
   G g;
   g.zero();
-  g.run(smem, T + (int64_t)i0 * npad + i0, npad, 64, T + (int64_t)i0 * npad + j0, npad, 64, npad - i0);
+  g.run(smem, T + (int64_t)i0 * npad + i0, npad, min(TILE, N - i0), T + (int64_t)i0 * npad + j0, npad, 64,
+        min(npad, (N + G::BK - 1) / G::BK * G::BK) - i0);
   // stage x rows and alpha of both blocks (aliases the pipeline buffers, free after run())
   const int ldx = d | 1;
   double* sxi = smem;

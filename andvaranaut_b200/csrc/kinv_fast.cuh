@@ -60,7 +60,11 @@ struct KinvFastLayout {
   }
 };
 
-using KinvG2 = TileGemm<64, 64, 16, 32, 32, 4, true, true>;
+#ifndef AVN_KINV_BK
+#define AVN_KINV_BK 16
+#define AVN_KINV_STAGES 4
+#endif
+using KinvG2 = TileGemm<64, 64, AVN_KINV_BK, 32, 32, AVN_KINV_STAGES, true, true>;
 
 template <int KIND, bool WITH_GX>
 __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
@@ -81,7 +85,10 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
   load_hyp(hyp, kd, theta + (int64_t)b * kd.P);
   G g;
   g.zero();
-  g.run(smem, T + (int64_t)i0 * npad + i0, npad, 64, T + (int64_t)i0 * npad + j0, npad, 64, npad - i0);
+  // rows >= N of T are those of the identity: the k range stops at N rounded up to the slab depth, and the
+  // padding rows of the last block row issue no DMMA
+  g.run(smem, T + (int64_t)i0 * npad + i0, npad, min(TILE, N - i0), T + (int64_t)i0 * npad + j0, npad, 64,
+        min(npad, (N + G::BK - 1) / G::BK * G::BK) - i0);
 
   // ---- stage the small operands (the pipeline buffers are free after run()) ----
   const KinvFastLayout lay(d);

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace avn {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -90,9 +92,12 @@ struct TileGemm {
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
 
-  // multiply-accumulate one staged k-slab (BK deep) from shared memory
+  // multiply-accumulate one staged k-slab (BK deep) from shared memory.  RAGGED: only the first mi_lim 8-row
+  // fragments of this warp are valid (last block row of a matrix whose size is not a tile multiple); the
+  // others issue no DMMA and keep their accumulators.
+  template <bool RAGGED>
   __device__ __forceinline__ void compute_stage(const double* sA, const double* sB, int wm,
-                                                int wn, int g, int t) {
+                                                int wn, int g, int t, int mi_lim) {
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       double a[MI], b[NI];
@@ -108,13 +113,17 @@ struct TileGemm {
       }
 #pragma unroll
       for (int i = 0; i < MI; i++)
+        if (!RAGGED || i < mi_lim) {
 #pragma unroll
-        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
   }
 
   // acc += A[., k0:k0+klen) * B[., k0:k0+klen)^T ; klen must be a multiple of BK.
   // Apt/Bpt point at (row 0, k = 0) of the respective tiles.  All threads of the CTA must call.
+  // Whole BM x BK / BN x BK tiles are always loaded (every caller works on tile-padded storage); a_rows < BM only
+  // says that the 8-row fragments from a_rows (rounded up) on are padding: they issue no DMMA.
   __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda,
                                       int a_rows, const double* Bpt, int64_t ldb, int b_rows, int klen) {
     run(smem, Apt, lda, a_rows, Bpt, ldb, b_rows, klen, [](int) {});
@@ -134,8 +143,8 @@ struct TileGemm {
       double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
       double* sB = sA + TA::SIZE;
       const int64_t koff = (int64_t)kt * BK;
-      load_operand<BM, BK, A_RC, NTHREADS>(sA, A_RC ? Apt + koff * lda : Apt + koff, lda, a_rows, tid);
-      load_operand<BN, BK, B_RC, NTHREADS>(sB, B_RC ? Bpt + koff * ldb : Bpt + koff, ldb, b_rows, tid);
+      load_operand<BM, BK, A_RC, NTHREADS>(sA, A_RC ? Apt + koff * lda : Apt + koff, lda, BM, tid);
+      load_operand<BN, BK, B_RC, NTHREADS>(sB, B_RC ? Bpt + koff * ldb : Bpt + koff, ldb, BN, tid);
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
@@ -145,17 +154,27 @@ struct TileGemm {
       }
       cp_async_commit();
     }
-    for (int kt = 0; kt < KT; kt++) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      int nk = kt + STAGES - 1;
-      if (nk < KT) {
-        pre_issue(nk);
-        issue(nk);
+    auto mainloop = [&](auto ragged_tag, int mi_lim) {
+      constexpr bool RAGGED = decltype(ragged_tag)::value;
+      for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        int nk = kt + STAGES - 1;
+        if (nk < KT) {
+          pre_issue(nk);
+          issue(nk);
+        }
+        cp_async_commit();
+        const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
+        compute_stage<RAGGED>(sA, sA + TA::SIZE, wm, wn, g, t, mi_lim);
       }
-      cp_async_commit();
-      const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-      compute_stage(sA, sA + TA::SIZE, wm, wn, g, t);
+    };
+    if (a_rows >= BM) {
+      mainloop(std::false_type{}, MI);
+    } else {  // same barrier sequence for every warp; warps past the last valid row only move data
+      int lim = (a_rows - wm * WM + 7) >> 3;
+      lim = lim < 0 ? 0 : (lim > MI ? MI : lim);
+      mainloop(std::true_type{}, lim);
     }
     cp_async_wait<0>();
     __syncthreads();
