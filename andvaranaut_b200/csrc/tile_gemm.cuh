@@ -92,17 +92,17 @@ struct TileGemm {
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
 
-  // multiply-accumulate one staged k-slab (BK deep) from shared memory.  RAGGED: only the first mi_lim 8-row
-  // fragments of this warp are valid (last block row of a matrix whose size is not a tile multiple); the
-  // others issue no DMMA and keep their accumulators.
-  template <bool RAGGED>
+  // multiply-accumulate one staged k-slab (BK deep) from shared memory; only the first MACT 8-row fragments of
+  // this warp are computed (MACT < MI: last block row of a matrix whose size is not a tile multiple -- the
+  // other fragments are padding and keep their accumulators).
+  template <int MACT>
   __device__ __forceinline__ void compute_stage(const double* sA, const double* sB, int wm,
-                                                int wn, int g, int t, int mi_lim) {
+                                                int wn, int g, int t) {
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double a[MI], b[NI];
+      double a[MACT], b[NI];
 #pragma unroll
-      for (int i = 0; i < MI; i++) {
+      for (int i = 0; i < MACT; i++) {
         int m = wm * WM + i * 8 + g;
         a[i] = A_RC ? sA[(kk + t) * TA::LD + m] : sA[m * TA::LD + kk + t];
       }
@@ -112,11 +112,9 @@ struct TileGemm {
         b[j] = B_RC ? sB[(kk + t) * TB::LD + n] : sB[n * TB::LD + kk + t];
       }
 #pragma unroll
-      for (int i = 0; i < MI; i++)
-        if (!RAGGED || i < mi_lim) {
+      for (int i = 0; i < MACT; i++)
 #pragma unroll
-          for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
+        for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
 
@@ -154,8 +152,10 @@ struct TileGemm {
       }
       cp_async_commit();
     }
-    auto mainloop = [&](auto ragged_tag, int mi_lim) {
-      constexpr bool RAGGED = decltype(ragged_tag)::value;
+    // mode 0: whole tile; 1: ragged -- this warp computes its first MI/2 fragments; 2: ragged -- all of them;
+    // 3: ragged -- none (the warp only moves data).  Every mode runs the same barrier sequence.
+    auto mainloop = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
       for (int kt = 0; kt < KT; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -166,15 +166,17 @@ struct TileGemm {
         }
         cp_async_commit();
         const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-        compute_stage<RAGGED>(sA, sA + TA::SIZE, wm, wn, g, t, mi_lim);
+        if constexpr (MODE == 0 || MODE == 2) compute_stage<MI>(sA, sA + TA::SIZE, wm, wn, g, t);
+        if constexpr (MODE == 1) compute_stage<(MI + 1) / 2>(sA, sA + TA::SIZE, wm, wn, g, t);
       }
     };
     if (a_rows >= BM) {
-      mainloop(std::false_type{}, MI);
-    } else {  // same barrier sequence for every warp; warps past the last valid row only move data
-      int lim = (a_rows - wm * WM + 7) >> 3;
-      lim = lim < 0 ? 0 : (lim > MI ? MI : lim);
-      mainloop(std::true_type{}, lim);
+      mainloop(std::integral_constant<int, 0>{});
+    } else {
+      const int lim = (a_rows - wm * WM + 7) >> 3;   // valid 8-row fragments of this warp
+      if (lim <= 0) mainloop(std::integral_constant<int, 3>{});
+      else if (lim <= (MI + 1) / 2) mainloop(std::integral_constant<int, 1>{});
+      else mainloop(std::integral_constant<int, 2>{});
     }
     cp_async_wait<0>();
     __syncthreads();
