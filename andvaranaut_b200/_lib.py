@@ -16,7 +16,7 @@ AVN_MAX_STAGES = 6
 AVN_MAX_WPARAMS = 8
 AVN_MAX_GH = 32
 AVN_TILE = 64
-PHASES = ('warp', 'cov', 'potrf', 'trsv', 'trtri', 'alpha', 'kinv_grad', 'finalize', 'kxs', 'predict_var')
+PHASES = ('warp', 'cov', 'factor', 'beta', 'unused4', 'alpha', 'kinv_grad', 'finalize', 'kxs', 'predict_var')
 
 KERNEL_IDS = {'RBF': 0, 'Matern52': 1, 'Matern32': 2, 'Exponential': 3, 'RatQuad': 4}
 OP_IDS = {'+': 0, '*': 1}

@@ -312,7 +312,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   fa.prof = prof_dev;
 #endif
   {
-    Phase ph(gp, AVN_PH_POTRF, st);
+    Phase ph(gp, AVN_PH_FACTOR, st);
     factor_kernel<<<grid, FAC_THREADS, FAC_SMEM_BYTES, st>>>(fa);
     LAUNCH_CHECK("factor_kernel");
   }
@@ -334,7 +334,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
 static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, bool want_alpha, cudaStream_t st) {
   const dim3 grid((unsigned)(npad / TILE), (unsigned)B);
   {
-    Phase ph(gp, AVN_PH_TRSV, st);
+    Phase ph(gp, AVN_PH_BETA, st);
     beta_kernel<<<grid, 256, 0, st>>>(W.t, W.z, (int)npad, W.beta, W.fpart);
     LAUNCH_CHECK("beta_kernel");
   }

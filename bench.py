@@ -92,8 +92,18 @@ def flops_ll(N, d):
 
 
 def flops_kinv_grad(N, d):
-    """algorithmic flops of the dominant kernel per sample: K^-1 tiles from T (N^3/3) + gradient contractions."""
+    """algorithmic flops of kinv_grad per sample: K^-1 tiles from T (N^3/3) + gradient contractions."""
     return N ** 3 / 3.0 + (3 * d + 4) * N ** 2 / 2.0
+
+
+def flops_factor(N):
+    """algorithmic flops of the dominant kernel per sample: Cholesky (N^3/3) + triangular inverse (N^3/3)."""
+    return 2.0 * N ** 3 / 3.0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE factor_kernel launch of the headline workload (B = 64) from the
+# `ncu --set full` capture summarised in profiles/r01f_ncu_factor_kinv_b64.json
+FACTOR_TRAFFIC_BYTES_B64 = 28.62e9 + 2.20e9
 
 
 def flops_predict(N, d, deg=8):
@@ -208,7 +218,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='hyperparameter samples per GPU per step (c2)')
@@ -320,25 +330,32 @@ def main():
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_value = world * B / (e2e_ms * 1e-3)
 
-    # ---- per-phase timing of the same step (separate, untimed repetitions) --------------------------
+    # ---- per-kernel timing: the same step repeated args.steps times with CUDA events around every launch
+    # (recorded by the library on the stream the kernels run on; one host sync per step to read them) ----
     eng.set_profiling(True)
     phases = {}
-    reps = 3
+    reps = args.steps
     for _ in range(reps):
         eng.loglik_grad(theta_dev, out=out)
         pm = eng.phase_ms()
         for k, v in pm.items():
             phases[k] = phases.get(k, 0.0) + v / reps
     eng.set_profiling(False)
-    kg_ms = phases['kinv_grad']
-    kg_flops = B * flops_kinv_grad(N, d)
-    achieved = kg_flops / (kg_ms * 1e-3) / 1e12
+    fk_ms = phases['factor']
+    fk_flops = B * flops_factor(N)
+    achieved = fk_flops / (fk_ms * 1e-3) / 1e12
+    kg_ach = B * flops_kinv_grad(N, d) / (phases['kinv_grad'] * 1e-3) / 1e12
     roofline = {
-        'bound': 'tensor', 'kernel': 'kinv_grad_kernel (K^-1 tiles via DMMA fused with the gradient contraction)',
-        'achieved': achieved, 'peak': p64, 'unit': 'TFLOP/s', 'frac': achieved / p64, 'traffic': None,
+        'bound': 'tensor',
+        'kernel': 'factor_kernel (persistent dataflow Cholesky + triangular inverse, FP64 DMMA tile products)',
+        'achieved': achieved, 'peak': p64, 'unit': 'TFLOP/s', 'frac': achieved / p64,
+        'traffic': FACTOR_TRAFFIC_BYTES_B64 if B == 64 else None,
         'peak_source': 'cuBLAS DGEMM fp64 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; '
                        'DMMA issue peak measured 37.0 TF, profiles/r01_microbench_fp64.jsonl)',
-        'algorithmic_flops_per_launch': kg_flops, 'kernel_ms': kg_ms,
+        'algorithmic_flops_per_launch': fk_flops, 'kernel_ms': fk_ms,
+        'second_kernel': {'kernel': 'kinv_grad_fast_kernel (K^-1 tiles fused with the gradient contraction)',
+                          'achieved': kg_ach, 'frac': kg_ach / p64, 'kernel_ms': phases['kinv_grad'],
+                          'algorithmic_flops_per_launch': B * flops_kinv_grad(N, d)},
         'step_frac': B * flops_ll(N, d) / (ms_per_step * 1e-3) / 1e12 / p64,
         'phase_ms': {k: round(v, 4) for k, v in phases.items() if v > 0},
     }

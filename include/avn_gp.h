@@ -141,7 +141,7 @@ int64_t avn_gp_last_launch_count(const avn_gp* gp);
  * CUDA events on the caller's stream around each phase; avn_gp_phase_ms synchronises on the last event and
  * returns the elapsed milliseconds of the most recent call, indexed by avn_phase. */
 enum avn_phase {
-  AVN_PH_WARP = 0, AVN_PH_COV = 1, AVN_PH_POTRF = 2, AVN_PH_TRSV = 3, AVN_PH_TRTRI = 4, AVN_PH_ALPHA = 5,
+  AVN_PH_WARP = 0, AVN_PH_COV = 1, AVN_PH_FACTOR = 2 /* chol + inverse */, AVN_PH_BETA = 3, AVN_PH_UNUSED4 = 4, AVN_PH_ALPHA = 5,
   AVN_PH_KINV_GRAD = 6, AVN_PH_FINALIZE = 7, AVN_PH_KXS = 8, AVN_PH_PREDICT_VAR = 9, AVN_PH_COUNT = 10
 };
 int avn_gp_set_profiling(avn_gp* gp, int enable);
