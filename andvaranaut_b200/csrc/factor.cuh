@@ -97,7 +97,6 @@ __device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t
     }
   }
   __syncthreads();
-  __threadfence();
 }
 
 // Slab-wise operand wait inside TileGemm::run: k-slab kt belongs to the 64-deep block m = m0 + kt / FAC_SPB, which
@@ -134,23 +133,40 @@ struct SlabWaiter {
     }
     __syncthreads();
     known = *s_known;
-    __threadfence();
   }
 };
 
-// all threads have written their part of a tile: make it visible, then publish the flag
+// All threads have written their part of a tile: publish the flag.  The barrier orders the CTA's stores before
+// thread 0's fence + release store (cumulativity), so one fence per CTA is enough; consumers read the flag with
+// ld.acquire in one thread, pass a barrier and read the data through L2 (cp.async.cg / ld.global.cg).
 __device__ __forceinline__ void publish(int32_t* flag, int value) {
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) st_release(flag, value);
-}
-__device__ __forceinline__ void publish2(int32_t* f0, int v0, int32_t* f1, int v1) {
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
+    st_release(flag, value);
+  }
+}
+__device__ __forceinline__ void publish2(int32_t* f0, int v0, int32_t* f1, int v1) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
     st_release(f0, v0);
     st_release(f1, v1);
   }
+}
+
+// accumulators <- minus a 64 x 64 global tile (the product then accumulates L L^T - A = -X on top of it)
+__device__ __forceinline__ void load_neg_tile(double (&acc)[4][4][2], const double* __restrict__ g, int64_t ld, int wm,
+                                              int wn, int gq, int t) {
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(g + (int64_t)r * ld + c));
+      acc[i][j][0] = -v.x;
+      acc[i][j][1] = -v.y;
+    }
 }
 
 // acc(m,n) += sum_c sA[m][c] * (B_KN ? sB[c][n] : sB[n][c]); 64x64x64 from shared memory, warp tile 32x32
@@ -183,23 +199,41 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64 x 64 diagonal block: Cholesky and triangular inverse, 128 threads, one barrier per column.
-// The block is held in registers as a 16 x 16 grid of 4 x 4 sub-blocks; thread (ty, tx), ty in 0..7, owns the
-// sub-blocks (ty, tx) and (ty + 8, tx).  Column j: its owners have published the (updated, unscaled) column in
-// vec[j & 1]; after the barrier every thread forms 1/sqrt(pivot) itself, the owners scale and keep the column,
-// everyone applies the rank-1 update to the columns right of j and the owners of column j+1 publish it.
-// sA holds A (lower part) on entry and L (zeros above the diagonal) on exit.
+// 64 x 64 diagonal block: Cholesky AND triangular inverse in one sweep, 128 threads, one barrier per column.
+// Elimination on [A | I] in place: L^-1 [A | I] = [L^T | L^-1].  The lower triangle is held in registers as a
+// 16 x 16 grid of 4 x 4 sub-blocks; thread (ty, tx), ty in 0..7, owns the sub-blocks (ty, tx) and (ty + 8, tx).
+// Before step j an entry (i, c) holds the partially eliminated A value if c >= j and the partially formed
+// T = L^-1 value if c < j.  Step j: the owners have published column j of A and row j of the T part in
+// vec[j & 1]; after the barrier every thread forms inv = 1/sqrt(A_jj) itself, then
+//   l_i = A_ij inv (saved to shared memory: column j of L),   T_jc = T_jc inv (c < j),   T_jj = inv,
+//   rows i > j:   A_ic -= l_i l_c (j < c <= i),   T_ic -= l_i T_jc (c < j),   T_ij = -l_i inv,
+// and the owners of column / row j+1 publish them for the next step.  64 dependent steps in all (the earlier
+// two-sweep version needed 128) and half the FP64 work per step.
+// sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void diag_chol_inv(double* sA, double* sT, double* vec /*[2][64]*/, double* dinv /*[64]*/,
-                                              double* dval /*[64]*/, int* s_bad, int pivot_base) {
+__device__ __forceinline__ void diag_chol_inv(double* sA, double* sT, double* vec /*[2][2][64]*/, double* dval /*[64]*/,
+                                              int* s_bad, int pivot_base) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double a[2][4][4];
 #pragma unroll
   for (int h = 0; h < 2; h++)
 #pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double2 v0 = *reinterpret_cast<const double2*>(&sA[(4 * (ty + 8 * h) + r) * FAC_LDS + 4 * tx]);
+      const double2 v1 = *reinterpret_cast<const double2*>(&sA[(4 * (ty + 8 * h) + r) * FAC_LDS + 4 * tx + 2]);
+      a[h][r][0] = v0.x; a[h][r][1] = v0.y; a[h][r][2] = v1.x; a[h][r][3] = v1.y;
+    }
+  __syncthreads();   // everyone holds its part of A: sA may now receive L
+  // zeros above the diagonal of L; column 0 of A for step 0
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+#pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
-      for (int c = 0; c < 4; c++) a[h][r][c] = sA[(4 * (ty + 8 * h) + r) * FAC_LDS + 4 * tx + c];
+      for (int c = 0; c < 4; c++) {
+        const int row = 4 * (ty + 8 * h) + r, col = 4 * tx + c;
+        if (col > row) sA[row * FAC_LDS + col] = 0.0;
+      }
   if (tx == 0) {
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -210,129 +244,92 @@ __device__ __forceinline__ void diag_chol_inv(double* sA, double* sT, double* ve
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       const int j = 4 * jb + jj;
-      double* vcur = vec + (j & 1) * TILE;
-      double* vnxt = vec + ((j + 1) & 1) * TILE;
+      const double* cur = vec + (j & 1) * 2 * TILE;        // [0..63] column j of A, [64..127] row j of the T part
+      double* nxt = vec + ((j + 1) & 1) * 2 * TILE;
       __syncthreads();
-      double piv = vcur[j];
+      double piv = cur[j];
       if (!(piv > 0.0)) {  // also catches NaN
         if (tid == 0 && *s_bad == 0) *s_bad = pivot_base + j + 1;
         piv = 1.0;
       }
       const double inv = rsqrt(piv);
-      if (tid == 0) {
-        dinv[j] = inv;
-        dval[j] = piv * inv;
-      }
+      if (tid == 0) dval[j] = piv * inv;
+      const int jn = (jj + 1) & 3;                // position of column / row j+1 inside its sub-block
+      const int jnb = (jj == 3) ? jb + 1 : jb;    // sub-block index of column / row j+1
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int vty = ty + 8 * h;
-        if (vty < jb || tx > vty) continue;   // rows above the pivot block / strictly upper sub-blocks
-        double lr[4], lc[4];
+        if (vty < jb || tx > vty) continue;   // rows above the pivot block / sub-blocks above the diagonal
+        double lr[4];
+        {
+          const double2 p0 = *reinterpret_cast<const double2*>(&cur[4 * vty]);
+          const double2 p1 = *reinterpret_cast<const double2*>(&cur[4 * vty + 2]);
+          lr[0] = p0.x * inv; lr[1] = p0.y * inv; lr[2] = p1.x * inv; lr[3] = p1.y * inv;
+        }
+        if (tx > jb) {
+          // all four columns are right of j and all four rows below it: plain rank-1 update of A
+          const double2 q0 = *reinterpret_cast<const double2*>(&cur[4 * tx]);
+          const double2 q1 = *reinterpret_cast<const double2*>(&cur[4 * tx + 2]);
+          const double lc[4] = {q0.x * inv, q0.y * inv, q1.x * inv, q1.y * inv};
 #pragma unroll
-        for (int r = 0; r < 4; r++) lr[r] = vcur[4 * vty + r] * inv;
+          for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) lc[c] = vcur[4 * tx + c] * inv;
-        if (tx == jb) {
+            for (int c = 0; c < 4; c++) a[h][r][c] = fma(-lr[r], lc[c], a[h][r][c]);
+        } else if (tx < jb) {
+          // all four columns are left of j: T part
+          const double2 q0 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx]);
+          const double2 q1 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx + 2]);
+          const double tr[4] = {q0.x * inv, q0.y * inv, q1.x * inv, q1.y * inv};   // final row j of T
 #pragma unroll
           for (int r = 0; r < 4; r++) {
             const int row = 4 * vty + r;
-            a[h][r][jj] = (row == j) ? piv * inv : (row > j ? lr[r] : a[h][r][jj]);
+            if (row > j) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) a[h][r][c] = fma(-lr[r], tr[c], a[h][r][c]);
+            } else if (row == j) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) a[h][r][c] = tr[c];
+            }
           }
-        }
+        } else {
+          // tx == jb: columns left of jj belong to the T part, column jj is turned from A into T, the rest is A
+          const double2 q0 = *reinterpret_cast<const double2*>(&cur[4 * tx]);
+          const double2 q1 = *reinterpret_cast<const double2*>(&cur[4 * tx + 2]);
+          const double2 t0 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx]);
+          const double2 t1 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx + 2]);
+          const double lc[4] = {q0.x * inv, q0.y * inv, q1.x * inv, q1.y * inv};
+          const double tr[4] = {t0.x * inv, t0.y * inv, t1.x * inv, t1.y * inv};
 #pragma unroll
-        for (int r = 0; r < 4; r++)
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            if (4 * tx + c > j && 4 * vty + r > j) a[h][r][c] = fma(-lr[r], lc[c], a[h][r][c]);
-        // publish column j+1 for the next step
-        if (jj < 3) {
-          if (tx == jb) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) vnxt[4 * vty + r] = a[h][r][jj + 1 > 3 ? 3 : jj + 1];
-          }
-        } else if (tx == jb + 1) {
-#pragma unroll
-          for (int r = 0; r < 4; r++) vnxt[4 * vty + r] = a[h][r][0];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // L to shared memory (zeros above the diagonal)
-#pragma unroll
-  for (int h = 0; h < 2; h++)
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int row = 4 * (ty + 8 * h) + r, col = 4 * tx + c;
-        sA[row * FAC_LDS + col] = (col <= row) ? a[h][r][c] : 0.0;
-      }
-  // ---- T = L^-1 by the same right-looking sweep on the rows of the identity: after step j-1 row j of the
-  // working matrix only misses the division by L_jj; its owners scale and publish it, then
-  // R[i,:] -= L[i,j] T[j,:] for the rows below. ----
-#pragma unroll
-  for (int h = 0; h < 2; h++)
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) a[h][r][c] = (4 * (ty + 8 * h) + r == 4 * tx + c) ? 1.0 : 0.0;
-  __syncthreads();
-  if (ty == 0) {   // row 0 of T
-    const double inv0 = dinv[0];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const double v = (4 * tx + c == 0) ? inv0 : 0.0;
-      a[0][0][c] = v;
-      vec[4 * tx + c] = v;
-    }
-  }
-  for (int jb = 0; jb < 16; jb++) {
-#pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      const int j = 4 * jb + jj;
-      const double* vcur = vec + (j & 1) * TILE;
-      double* vnxt = vec + ((j + 1) & 1) * TILE;
-      __syncthreads();
-      const double invn = (j + 1 < TILE) ? dinv[j + 1] : 0.0;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int vty = ty + 8 * h;
-        if (vty < jb || tx > vty) continue;
-        double tc[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) tc[c] = vcur[4 * tx + c];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          const int row = 4 * vty + r;
-          if (row > j) {
-            const double lij = sA[row * FAC_LDS + j];
-#pragma unroll
-            for (int c = 0; c < 4; c++) a[h][r][c] = fma(-lij, tc[c], a[h][r][c]);
-          }
-        }
-        // owners of row j+1: scale by 1/L_{j+1,j+1}, keep and publish
-        const int jn = j + 1;
-        if (jn < TILE && vty == (jn >> 2)) {
-          const int rn = (jj + 1) & 3;
-#pragma unroll
-          for (int r = 0; r < 4; r++)
-            if (r == rn) {
+          for (int r = 0; r < 4; r++) {
+            const int row = 4 * vty + r;
+            if (row > j) {
 #pragma unroll
               for (int c = 0; c < 4; c++) {
-                const double v = (4 * tx + c <= jn) ? a[h][r][c] * invn : 0.0;
-                a[h][r][c] = v;
-                vnxt[4 * tx + c] = v;
+                if (c < jj) a[h][r][c] = fma(-lr[r], tr[c], a[h][r][c]);
+                else if (c == jj) a[h][r][c] = -lr[r] * inv;
+                else a[h][r][c] = fma(-lr[r], lc[c], a[h][r][c]);
               }
-            }
-        }
-      }
-      // sub-blocks right of the diagonal never run the loop body: their share of the published row is zero
-      if (j + 1 < TILE) {
-        const int vt = (j + 1) >> 2;
-        if ((ty == (vt & 7)) && tx > vt) {
+              sA[row * FAC_LDS + j] = lr[r];
+            } else if (row == j) {
 #pragma unroll
-          for (int c = 0; c < 4; c++) vnxt[4 * tx + c] = 0.0;
+              for (int c = 0; c < 4; c++) {
+                if (c < jj) a[h][r][c] = tr[c];
+                else if (c == jj) a[h][r][c] = inv;
+              }
+              sA[row * FAC_LDS + j] = piv * inv;
+            }
+          }
+        }
+        // publish column j+1 of A and row j+1 of the T part (columns <= j) for the next step
+        if (j + 1 < TILE) {
+          if (tx == jnb) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) nxt[4 * vty + r] = a[h][r][jn];
+          }
+          if (vty == jnb && tx <= jb) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) nxt[TILE + 4 * tx + c] = a[h][jn][c];
+          }
         }
       }
     }
@@ -354,8 +351,8 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
   __shared__ int s_ticket;
   __shared__ int s_known;
   __shared__ int s_bad;
-  __shared__ __align__(16) double s_vec[2 * TILE];
-  __shared__ double s_dinv[TILE], s_dval[TILE];
+  __shared__ __align__(16) double s_vec[4 * TILE];
+  __shared__ double s_dval[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % 2, wn = warp / 2, gq = lane >> 2, t = lane & 3;
   const int npad = fa.npad, nb = fa.nb, B = fa.B;
@@ -402,26 +399,27 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
     const int rows_k = min(TILE, fa.n - k0);   // valid rows of block row k
     if (type == 0) {
       // ---------------- D(b,k) ----------------
-      FacKK g;
-      g.zero();
-      if (k > 0) {
-        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
-        g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); });
-        FPROF(2);
-      }
       double* Akk = L + (int64_t)k0 * npad + k0;
       double* Tkk = T + (int64_t)k0 * npad + k0;
+      FacKK g;
+      load_neg_tile(g.acc, Akk, npad, wm, wn, gq, t);
+      if (k > 0) {
+        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
+        // only the lower triangle of the block is used: the warp of the upper-right quadrant computes nothing
+        g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); },
+              (wm == 0 && wn == 1) ? 0x7fffffff : 0);
+        FPROF(2);
+      }
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-          const double2 v = __ldcg(reinterpret_cast<const double2*>(Akk + (int64_t)r * npad + c));
-          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(v.x - g.acc[i][j][0], v.y - g.acc[i][j][1]);
+          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
         }
       if (tid == 0) s_bad = __ldcg(fa.info + b);
       __syncthreads();
-      diag_chol_inv(sA, sB, s_vec, s_dinv, s_dval, &s_bad, k0);
+      diag_chol_inv(sA, sB, s_vec, s_dval, &s_bad, k0);
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
         *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sA[r * FAC_LDS + c]);
@@ -440,22 +438,21 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
     } else if (type == 1) {
       // ---------------- P(b,k,i) ----------------
       const int i = idx, i0 = i * TILE;
+      double* Aik = L + (int64_t)i0 * npad + k0;
       FacKK g;
-      g.zero();
+      load_neg_tile(g.acc, Aik, npad, wm, wn, gq, t);
       if (k > 0) {
         SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0};
         g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
               [&](int kt) { w(kt); });
         FPROF(2);
       }
-      double* Aik = L + (int64_t)i0 * npad + k0;
 #pragma unroll
       for (int ii = 0; ii < 4; ii++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-          const double2 v = __ldcg(reinterpret_cast<const double2*>(Aik + (int64_t)r * npad + c));
-          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(v.x - g.acc[ii][j][0], v.y - g.acc[ii][j][1]);
+          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
         }
       FPROF(4);
       wait_flag(lflag + k, k + 1, fa.ctl);   // T[k,k] is there (also orders the sA writes)
@@ -480,8 +477,9 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       FacKR g;
       g.zero();
       SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0};
+      // first slab: B = T[j,j] is lower triangular, its columns n >= 32 vanish for the first 32 k
       g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
-            [&](int kt) { w(kt); });
+            [&](int kt) { w(kt); }, wn == 1 ? 32 / FAC_BK : 0);
       FPROF(2);
 #pragma unroll
       for (int ii = 0; ii < 4; ii++)

@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
   g.zero();
   // rows >= N of T are those of the identity: the k range stops at N rounded up to the slab depth, and the
   // padding rows of the last block row issue no DMMA
+  // first slab: A = T[i,i] is lower triangular, its columns m >= 32 vanish for the first 32 k
   g.run(smem, T + (int64_t)i0 * npad + i0, npad, min(TILE, N - i0), T + (int64_t)i0 * npad + j0, npad, 64,
-        min(npad, (N + G::BK - 1) / G::BK * G::BK) - i0);
+        min(npad, (N + G::BK - 1) / G::BK * G::BK) - i0, [](int) {}, ((threadIdx.x >> 5) % G::WARPS_M) == 1 ? 32 / G::BK : 0);
 
   // ---- stage the small operands (the pipeline buffers are free after run()) ----
   const KinvFastLayout lay(d);

@@ -129,9 +129,11 @@ struct TileGemm {
 
   // As above; pre_issue(kt) is called by every thread (uniformly) before the loads of k-slab kt are issued,
   // so that a dataflow kernel can wait for operands that other CTAs are still producing.
+  // skip_kt: this warp issues no DMMA for the first skip_kt k-slabs (its part of the operands is known to be
+  // zero there: triangular diagonal blocks); it still takes part in the loads and barriers.
   template <typename PreIssue>
   __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda, int a_rows, const double* Bpt,
-                                      int64_t ldb, int b_rows, int klen, PreIssue pre_issue) {
+                                      int64_t ldb, int b_rows, int klen, PreIssue pre_issue, int skip_kt = 0) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
@@ -166,8 +168,10 @@ struct TileGemm {
         }
         cp_async_commit();
         const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-        if constexpr (MODE == 0 || MODE == 2) compute_stage<MI>(sA, sA + TA::SIZE, wm, wn, g, t);
-        if constexpr (MODE == 1) compute_stage<(MI + 1) / 2>(sA, sA + TA::SIZE, wm, wn, g, t);
+        if (kt >= skip_kt) {
+          if constexpr (MODE == 0 || MODE == 2) compute_stage<MI>(sA, sA + TA::SIZE, wm, wn, g, t);
+          if constexpr (MODE == 1) compute_stage<(MI + 1) / 2>(sA, sA + TA::SIZE, wm, wn, g, t);
+        }
       }
     };
     if (a_rows >= BM) {
