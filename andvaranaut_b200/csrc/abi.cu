@@ -2,6 +2,7 @@
 // See include/avn_gp.h for the contract and the reference call sites each entry point replaces.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 
 #include "kernels.cuh"
@@ -284,6 +285,7 @@ static int factor_grid(int64_t total_tasks, int* out) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES);
     if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
     resident = sms * per_sm;
+    if (const char* e = getenv("AVN_FAC_CTAS_PER_SM")) resident = sms * atoi(e);   // development knob
   }
   *out = (int)(total_tasks < resident ? total_tasks : resident);
   return 0;
@@ -303,7 +305,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info;
   fa.lflag = W.lflag; fa.tflag = W.tflag; fa.ctl = W.ctl;
   fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.n = (int)gp->N; fa.want_inverse = want_inverse ? 1 : 0;
-  fa.dgap = (int)((2 * (int64_t)grid + B - 1) / B);
+  fa.dgap = 0;   // D(.,s+1) right behind P(.,s,s+1): its first s slabs are final already, only the last one waits
   fa.prof = nullptr;
 #ifdef AVN_FACTOR_PROF
   static long long* prof_dev = nullptr;
