@@ -185,3 +185,33 @@ def test_prior_logps_match_scipy():
     assert np.allclose(go.logp_normal(x, 0.0, 1.0), st.norm().logpdf(x))
     a, b = (1e-3 - 0.5) / 0.15, (100 - 0.5) / 0.15
     assert np.allclose(go.logp_truncnormal(x, 0.5, 0.15, 1e-3, 100.0), st.truncnorm(a, b, loc=0.5, scale=0.15).logpdf(x))
+
+
+# ---- independent pin of the GP algebra: scikit-learn's GaussianProcessRegressor (installed here) ----------------
+# PyMC itself cannot be installed offline, so the oracle's kernel / marginal-likelihood / conditional formulas are
+# checked against a second, unrelated implementation of the same textbook algebra.  sklearn parameterises in log
+# space (gradient = theta * d/dtheta) and evaluates Matern kernels at the exact distance, PyMC at sqrt(r2 + 1e-12):
+# the two differ by ~1e-12 relative on the diagonal, hence the 1e-8 tolerances for the Matern cases.
+@pytest.mark.parametrize('kern,tol', [('RBF', 1e-10), ('Matern52', 1e-8), ('Matern32', 1e-8)])
+def test_oracle_matches_scikit_learn_gp(kern, tol):
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, Matern, ConstantKernel, WhiteKernel
+    d, N, M = 3, 60, 25
+    spec = go.ModelSpec(nx=d, kerns=[kern], noise=True, jitter=1e-6)
+    X, y, th, Xs = cases.synth(spec, N, seed=31, M=M)
+    p = go.unpack(spec, th)
+    base = RBF(length_scale=p['l']) if kern == 'RBF' else Matern(length_scale=p['l'], nu=2.5 if kern == 'Matern52' else 1.5)
+    k = ConstantKernel(p['kv'][0]) * base + WhiteKernel(p['gv'])
+    gpr = GaussianProcessRegressor(kernel=k, alpha=spec.jitter, optimizer=None).fit(X, y)
+    lml, glog = gpr.log_marginal_likelihood(gpr.kernel_.theta, eval_gradient=True)
+    r = go.loglik(spec, th, X, y)
+    assert abs(r.ll - lml) <= tol * abs(lml)
+    # sklearn's theta order: log kv, log l[0..d-1], log gv
+    o = spec.offsets()
+    g_sk = np.concatenate([[glog[-1] / p['gv']], glog[1:1 + d] / p['l'], [glog[0] / p['kv'][0]]])
+    g_or = np.concatenate([[r.grad[o['gv']]], r.grad[o['l']:o['l'] + d], [r.grad[o['kv']]]])
+    assert np.max(np.abs(g_or - g_sk) / np.maximum(np.abs(g_sk), 1e-3 * np.max(np.abs(g_sk)))) <= max(tol, 1e-9) * 10
+    mu_sk, sd_sk = gpr.predict(Xs, return_std=True)           # includes the WhiteKernel term: pred_noise=True
+    mu, var = go.predict(spec, th, X, y, Xs)
+    assert np.max(np.abs(mu - mu_sk)) <= 1e-7 * np.max(np.abs(mu_sk))
+    assert np.max(np.abs(var - sd_sk ** 2) / np.maximum(sd_sk ** 2, p['kv'][0])) <= 1e-7
