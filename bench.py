@@ -433,6 +433,13 @@ def main():
                                            f'in blocks of {Msub} per GPU', 'scaling': 'weak',
                                'frac_of_fp64_peak': world * Msub * flops_predict(8192, 10) / (ms4 * 1e-3) / 1e12 / (p64 * world),
                                'factorize_ms': fact_ms, 'info': int(info4[0])}
+        # c5: Bayesian-optimisation iterations through the GPMCMC API (rank 0 only: one sequential optimiser)
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import c5_bo_probe
+            extra['c5_bo'] = {'metric': 'bo_iterations_per_s', 'workload': 'd=12, 4096 LHC candidates -> EI -> argmax -> '
+                              'append -> warm-started MAP refit, at three training-set sizes (3 iterations each)',
+                              'sizes': [c5_bo_probe.run(n) for n in (256, 1024, 4096)]}
         line['extra'] = extra
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
