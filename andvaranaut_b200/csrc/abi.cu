@@ -268,7 +268,20 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
     cudaError_t e = opt_in_smem(cov_kernel, smem);
     if (e != cudaSuccess) return fail_cuda("cov_kernel smem", e);
   }
-  cov_kernel<<<dim3((unsigned)ntiles, (unsigned)B), 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout);
+  const dim3 grid((unsigned)ntiles, (unsigned)B);
+  if (kd.nkern == 1 && smem <= 48 * 1024) {
+    // single-kernel models: instantiation per kernel kind (no switch / fold inside the element loop)
+    switch (kd.kern[0]) {
+      case AVN_RBF: cov1_kernel<AVN_RBF><<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout); break;
+      case AVN_MATERN52: cov1_kernel<AVN_MATERN52><<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout); break;
+      case AVN_MATERN32: cov1_kernel<AVN_MATERN32><<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout); break;
+      case AVN_EXPONENTIAL: cov1_kernel<AVN_EXPONENTIAL><<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout); break;
+      default: cov1_kernel<AVN_RATQUAD><<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout); break;
+    }
+    LAUNCH_CHECK("cov1_kernel");
+    return 0;
+  }
+  cov_kernel<<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout);
   LAUNCH_CHECK("cov_kernel");
   return 0;
 }

@@ -191,6 +191,88 @@ __global__ void __launch_bounds__(256, AVN_COV_MINB) cov_kernel(KernDesc kd, int
   }
 }
 
+// Single-kernel models (nkern == 1), kernel kind known at compile time: the same tile and thread mapping, but the
+// element loop holds no switch, no kernel fold and the trimmed exp (avn_dev.cuh).
+template <int KIND>
+__global__ void __launch_bounds__(256, AVN_COV_MINB) cov1_kernel(KernDesc kd, int N, int npad, const double* __restrict__ theta,
+                                                                 const double* __restrict__ xs_all,
+                                                                 const double* __restrict__ x2_all, double* __restrict__ Kout) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  int ti, tj;
+  tri_index(blockIdx.x, ti, tj);
+  const int i0 = ti * TILE, j0 = tj * TILE;
+  const int d = kd.d;
+  const double* th = theta + (int64_t)b * kd.P;
+  const double kvk = th[kd.off_kv];
+  const double dadd = (kd.noise ? th[kd.off_gv] : 0.0) + kd.jitter;
+  const double alpha = kd.has_alpha ? th[kd.off_alpha] : 1.0;
+  double* sxi = smem;                 // [d][64]
+  double* sxj = sxi + d * TILE;       // [d][64]
+  double* s2i = sxj + d * TILE;
+  double* s2j = s2i + TILE;
+  const double* xs = xs_all + (int64_t)b * npad * d;
+  const double* x2 = x2_all + (int64_t)b * npad;
+  for (int e = tid; e < TILE * d; e += 256) {
+    const int r = e / d, m = e - r * d;
+    sxi[m * TILE + r] = xs[(int64_t)i0 * d + e];
+    sxj[m * TILE + r] = xs[(int64_t)j0 * d + e];
+  }
+  if (tid < TILE) s2i[tid] = x2[i0 + tid];
+  else if (tid < 2 * TILE) s2j[tid - TILE] = x2[j0 + tid - TILE];
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double dot[4][4];
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) dot[rr][cc] = 0.0;
+  for (int m = 0; m < d; m++) {
+    const double2* pi = reinterpret_cast<const double2*>(sxi + m * TILE + ty * 4);
+    const double2* pj = reinterpret_cast<const double2*>(sxj + m * TILE + tx * 4);
+    const double2 a0 = pi[0], a1 = pi[1], b0 = pj[0], b1 = pj[1];
+    const double xi[4] = {a0.x, a0.y, a1.x, a1.y}, xj[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) dot[rr][cc] = fma(xi[rr], xj[cc], dot[rr][cc]);   // sequential in m
+  }
+  double n2i[4], n2j[4];
+  {
+    const double2* pi = reinterpret_cast<const double2*>(s2i + ty * 4);
+    const double2* pj = reinterpret_cast<const double2*>(s2j + tx * 4);
+    const double2 a0 = pi[0], a1 = pi[1], b0 = pj[0], b1 = pj[1];
+    n2i[0] = a0.x; n2i[1] = a0.y; n2i[2] = a1.x; n2i[3] = a1.y;
+    n2j[0] = b0.x; n2j[1] = b0.y; n2j[2] = b1.x; n2j[3] = b1.y;
+  }
+  double* Kb = Kout + (int64_t)b * npad * npad;
+  const bool interior = (ti != tj) && (i0 + TILE <= N);   // no diagonal, no padding (j0 < i0)
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int I = i0 + ty * 4 + rr;
+    double out[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      double r2 = __dadd_rn(__dmul_rn(-2.0, dot[rr][cc]), __dadd_rn(n2i[rr], n2j[cc]));
+      r2 = r2 > 0.0 ? r2 : 0.0;
+      double kk, dk;
+      kern_val_fast<KIND, false>(r2, alpha, kk, dk);
+      out[cc] = __dmul_rn(kvk, kk);
+    }
+    if (!interior) {
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        const int J = j0 + tx * 4 + cc;
+        if (I >= N || J >= N) out[cc] = (I == J) ? 1.0 : 0.0;
+        else if (I == J) out[cc] += dadd;
+      }
+    }
+    double2* dst = reinterpret_cast<double2*>(Kb + (int64_t)I * npad + j0 + tx * 4);
+    dst[0] = make_double2(out[0], out[1]);
+    dst[1] = make_double2(out[2], out[3]);
+  }
+}
+
 // K2 (Cholesky + triangular inverse + beta) lives in factor.cuh.
 
 // alpha = T^T beta.  grid (nb, B), 256 threads.

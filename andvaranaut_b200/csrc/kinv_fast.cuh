@@ -15,32 +15,6 @@
 
 namespace avn {
 
-template <int KIND>
-__device__ __forceinline__ void kern_val_t(double r2, double alpha, double& k, double& dk) {
-  if constexpr (KIND == AVN_RBF) {
-    k = exp(-0.5 * r2);
-    dk = -0.5 * k;
-  } else if constexpr (KIND == AVN_MATERN52) {
-    double r = sqrt(r2 + 1e-12);
-    double e = exp(-kSqrt5 * r);
-    k = (1.0 + kSqrt5 * r + (5.0 / 3.0) * (r * r)) * e;
-    dk = -(5.0 / 6.0) * (1.0 + kSqrt5 * r) * e;
-  } else if constexpr (KIND == AVN_MATERN32) {
-    double r = sqrt(r2 + 1e-12);
-    double e = exp(-kSqrt3 * r);
-    k = (1.0 + kSqrt3 * r) * e;
-    dk = -1.5 * e;
-  } else if constexpr (KIND == AVN_EXPONENTIAL) {
-    double r = sqrt(r2 + 1e-12);
-    k = exp(-0.5 * r);
-    dk = -k / (4.0 * r);
-  } else {
-    double base = 1.0 + 0.5 * r2 * (1.0 / alpha);
-    k = pow(base, -alpha);
-    dk = -0.5 * k / base;
-  }
-}
-
 struct KinvFastLayout {
   int dpad, lds, np, lda, ldp;
   int off_w, off_xsi, off_xsj, off_xai, off_xaj, off_vec, total;  // in doubles
@@ -164,7 +138,7 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
         double r2 = (sx2i[r] + sx2j[c]) - 2.0 * U[i][j][h];
         r2 = r2 > 0.0 ? r2 : 0.0;
         double kk_, dk_;
-        kern_val_t<KIND>(r2, alpha, kk_, dk_);
+        kern_val_fast<KIND, true>(r2, alpha, kk_, dk_);
         skv = fma(w, kk_, skv);
         wkv[h] = w * kvk * dk_;
         if constexpr (KIND == AVN_RATQUAD) {
