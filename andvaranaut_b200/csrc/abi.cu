@@ -682,3 +682,73 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   }
   return 0;
 }
+
+// ---- predict with gradients w.r.t. the query points (BO refine) -------------------------------------
+extern "C" size_t avn_gp_predict_grad_workspace_bytes(const avn_gp* gp, int64_t M) {
+  return 2 * avn_gp_predict_workspace_bytes(gp, M);
+}
+
+extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const double* Xs_dev, int64_t M,
+                                   const avn_epilogue* epi, int32_t pred_noise, const double* mean_add_dev,
+                                   const double* dmean_add_dev, double* out_mean_dev, double* out_var_dev,
+                                   double* out_dmean_dev, double* out_dvar_dev, void* ws_dev, size_t ws_bytes,
+                                   void* stream) {
+  if (!gp || !state_dev || !Xs_dev || !epi || !out_mean_dev || !out_var_dev || !out_dmean_dev || !out_dvar_dev || !ws_dev)
+    return fail("avn_gp_predict_grad: null argument");
+  if (gp->N < 1) return fail("avn_gp_predict_grad: set_data first");
+  if (M < 1) return fail("avn_gp_predict_grad: M must be >= 1");
+  if (epi->mode < 0 || epi->mode > 2) return fail("avn_gp_predict_grad: bad epilogue mode");
+  if (epi->mode != 0 && (epi->deg < 1 || epi->deg > AVN_MAX_GH))
+    return fail("avn_gp_predict_grad: deg out of range [1,32]");
+  const KernDesc& kd = gp->kd;
+  const int64_t npad = npad_of(gp->N);
+  StateLayout S = state_layout(gp);
+  const int64_t cols_cap = (int64_t)(ws_bytes / (2 * npad * 8)) / TILE * TILE;
+  if (cols_cap < TILE) return fail("avn_gp_predict_grad: workspace too small");
+  gp->launches = 0;
+  phases_reset(gp);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* sb = static_cast<const char*>(state_dev);
+  const HypS* hyp = reinterpret_cast<const HypS*>(sb + S.hyp);
+  const double* alpha = reinterpret_cast<const double*>(sb + S.alpha);
+  const double* xs = reinterpret_cast<const double*>(sb + S.xs);
+  const double* x2 = reinterpret_cast<const double*>(sb + S.x2);
+  const double* T = reinterpret_cast<const double*>(sb + S.t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = opt_in_smem(predict_v_kernel, PredG::SMEM_BYTES);
+    if (e == cudaSuccess) e = opt_in_smem(ttv_kernel, TtvG::SMEM_BYTES);
+    if (e != cudaSuccess) return fail_cuda("predict_grad smem opt-in", e);
+    attr_done = true;
+  }
+  const size_t smem_kxs = (size_t)(kd.nkern * TILE * (kd.d | 1) + kd.nkern * TILE) * 8;
+  const size_t smem_pg = smem_kxs + (size_t)(4 * TILE * 2 * kd.d) * 8;
+  if (smem_pg > 48 * 1024) {
+    cudaError_t e = opt_in_smem(predict_grad_kernel, smem_pg);
+    if (e != cudaSuccess) return fail_cuda("predict_grad_kernel smem", e);
+  }
+  for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
+    const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
+    const unsigned nblk = (unsigned)(cols / TILE);
+    double* Kxs = static_cast<double*>(ws_dev);          // K_xs, later W = K^-1 K_xs
+    double* V = Kxs + npad * cols;
+    {
+      Phase ph(gp, AVN_PH_KXS, st);
+      kxs_kernel<<<nblk, 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols,
+                                              Kxs, out_mean_dev);
+      LAUNCH_CHECK("kxs_kernel");
+    }
+    Phase ph2(gp, AVN_PH_PREDICT_VAR, st);
+    predict_v_kernel<<<nblk, PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0,
+                                                                       pred_noise ? 1 : 0, V, out_var_dev);
+    LAUNCH_CHECK("predict_v_kernel");
+    ttv_kernel<<<dim3(nblk, (unsigned)(npad / TILE)), TtvG::NTHREADS, TtvG::SMEM_BYTES, st>>>((int)npad, T, V, (int)cols,
+                                                                                             Kxs);
+    LAUNCH_CHECK("ttv_kernel");
+    predict_grad_kernel<<<nblk, 256, smem_pg, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Kxs, (int)cols, Xs_dev,
+                                                    M, m0, *epi, mean_add_dev, dmean_add_dev, out_mean_dev, out_var_dev,
+                                                    out_dmean_dev, out_dvar_dev);
+    LAUNCH_CHECK("predict_grad_kernel");
+  }
+  return 0;
+}

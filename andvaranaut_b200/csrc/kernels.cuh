@@ -715,6 +715,240 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc k
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4': predict with gradients w.r.t. the (converted) query points -- the BO refine graph of the reference
+// (gpmcmc.py:738-801: kstar, v = L^-1 kstar, mean = kstar^T alpha, var = k** - v^T v, Gauss-Hermite reversion,
+// EI; differentiated by PyTensor inside pm.find_MAP over x).  Here analytically:
+//   d mu / d x_m = sum_i alpha_i dk_i/dx_m,   d s2 / d x_m = -2 sum_i w_i dk_i/dx_m,   w = T^T (T k*) = K^-1 k*,
+//   dk_i/dx_m = sum_q coef_q kv_q k_q'(r2_q) 2 (xs*_qm - xs_qim) / l_qm   (coef_q: product rule of the kernel fold)
+// and the chain rule through the reversion epilogue.
+//   (a) kxs_kernel           K_xs panel + latent mean                     (as predict)
+//   (b) predict_v_kernel     V = T K_xs stored, latent variance           (DMMA)
+//   (c) ttv_kernel           W = T^T V                                    (DMMA), overwrites the K_xs panel
+//   (d) predict_grad_kernel  the O(N d) contractions per point + epilogue chain
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PredG::NTHREADS) predict_v_kernel(KernDesc kd, int npad, const HypS* __restrict__ hyp_g,
+                                                                    const double* __restrict__ T,
+                                                                    const double* __restrict__ Kxs, int mld, int64_t M,
+                                                                    int64_t m_begin, int pred_noise,
+                                                                    double* __restrict__ V, double* __restrict__ var_out) {
+  using G = PredG;
+  extern __shared__ double smem[];
+  __shared__ double colsq[2][TILE];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int nb = npad / TILE;
+  double cs[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  G g;
+  for (int ib = 0; ib < nb; ib++) {
+    g.zero();
+    g.run(smem, T + (int64_t)ib * TILE * npad, npad, 64, Kxs + col0, mld, 64, (ib + 1) * TILE);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cs[j][0] = fma(g.acc[i][j][0], g.acc[i][j][0], cs[j][0]);
+        cs[j][1] = fma(g.acc[i][j][1], g.acc[i][j][1], cs[j][1]);
+        const int r = ib * TILE + wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+        *reinterpret_cast<double2*>(V + (int64_t)r * mld + col0 + c) = make_double2(g.acc[i][j][0], g.acc[i][j][1]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      double v = cs[j][h];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (gq == 0) colsq[wm][wn * 32 + j * 8 + 2 * t + h] = v;
+    }
+  __syncthreads();
+  if (tid < TILE) {
+    const int64_t mg = m_begin + col0 + tid;
+    if (mg < M) {
+      const HypS& hyp = *hyp_g;
+      double var = kdiag_total(kd, hyp) - (colsq[0][tid] + colsq[1][tid]);
+      if (pred_noise) var += hyp.gv;
+      var_out[mg] = var;
+    }
+  }
+}
+
+using TtvG = TileGemm<64, 64, 16, 32, 32, 4, true, true>;
+
+// W[i,:] = sum_{k >= i} T[k,i]^T V[k,:].  grid (column blocks, nb), 128 threads.
+__global__ void __launch_bounds__(TtvG::NTHREADS) ttv_kernel(int npad, const double* __restrict__ T,
+                                                             const double* __restrict__ V, int mld,
+                                                             double* __restrict__ W) {
+  using G = TtvG;
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int i0 = blockIdx.y * TILE;
+  G g;
+  g.zero();
+  g.run(smem, T + (int64_t)i0 * npad + i0, npad, 64, V + (int64_t)i0 * mld + col0, mld, 64, npad - i0);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = i0 + wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+      *reinterpret_cast<double2*>(W + (int64_t)r * mld + col0 + c) = make_double2(g.acc[i][j][0], g.acc[i][j][1]);
+    }
+}
+
+// grid (column blocks), 256 threads = 4 row groups x 64 test points.
+__global__ void __launch_bounds__(256) predict_grad_kernel(KernDesc kd, int N, int npad, const HypS* __restrict__ hyp_g,
+                                                           const double* __restrict__ xs_tr,
+                                                           const double* __restrict__ x2_tr,
+                                                           const double* __restrict__ alpha,
+                                                           const double* __restrict__ Wm, int mld,
+                                                           const double* __restrict__ Xtest, int64_t M, int64_t m_begin,
+                                                           avn_epilogue epi, const double* __restrict__ mean_add,
+                                                           const double* __restrict__ dmean_add,
+                                                           double* __restrict__ mu_io, double* __restrict__ var_io,
+                                                           double* __restrict__ dmean_out, double* __restrict__ dvar_out) {
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  const int tid = threadIdx.x, c = tid & 63, rg = tid >> 6;
+  const int d = kd.d, nk = kd.nkern;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int64_t mg = m_begin + col0 + c;
+  for (int e = tid; e < (int)(sizeof(HypS) / sizeof(double)); e += 256)
+    reinterpret_cast<double*>(&hyp)[e] = reinterpret_cast<const double*>(hyp_g)[e];
+  __syncthreads();
+  const int ldx = d | 1;
+  double* sx = smem;                       // [nk][64][ldx] scaled test points
+  double* sx2 = sx + nk * TILE * ldx;      // [nk][64]
+  double* sred = sx2 + nk * TILE;          // [4][64][2 * d] partial sums of the row groups
+  if (rg == 0) {
+    for (int k = 0; k < nk; k++) {
+      double tmp[MAXD];
+      for (int m = 0; m < d; m++) {
+        const double x = (mg < M) ? Xtest[mg * d + m] : 0.0;
+        tmp[m] = __dmul_rn(x, hyp.invl[k][m]);
+        sx[(k * TILE + c) * ldx + m] = tmp[m];
+      }
+      sx2[k * TILE + c] = sumsq_numpy_order(tmp, d);
+    }
+  }
+  __syncthreads();
+  double gmu[MAXD], gs[MAXD];
+#pragma unroll
+  for (int m = 0; m < MAXD; m++) gmu[m] = gs[m] = 0.0;
+  for (int n = rg; n < N; n += 4) {
+    // kernel values / derivatives of every kernel of the fold at the pair (train n, test c)
+    double vals[MAXK], dks[MAXK];
+    for (int q = 0; q < nk; q++) {
+      const double r2 = sqdist_gram(xs_tr + ((int64_t)q * npad + n) * d, sx + (q * TILE + c) * ldx,
+                                    x2_tr[(int64_t)q * npad + n], sx2[q * TILE + c], d);
+      double kq, dkq;
+      kern_val(kd.kern[q], r2, hyp.alpha, kq, dkq);
+      vals[q] = hyp.kv[q] * kq;
+      dks[q] = (r2 > 0.0) ? hyp.kv[q] * dkq : 0.0;   // the clip of square_dist has zero slope where it is active
+    }
+    // coef[q] = d fold / d vals[q] through the left-to-right fold (as in kinv_grad_kernel)
+    double coef[MAXK];
+    {
+      double prefs[MAXK];
+      prefs[0] = vals[0];
+      for (int q = 1; q < nk; q++) prefs[q] = (kd.op[q - 1] == AVN_ADD) ? prefs[q - 1] + vals[q] : prefs[q - 1] * vals[q];
+      double gg = 1.0;
+      for (int q = nk - 1; q >= 1; q--) {
+        if (kd.op[q - 1] == AVN_ADD) {
+          coef[q] = gg;
+        } else {
+          coef[q] = gg * prefs[q - 1];
+          gg *= vals[q];
+        }
+      }
+      coef[0] = gg;
+    }
+    const double an = alpha[n], wn_ = Wm[(int64_t)n * mld + col0 + c];
+    for (int q = 0; q < nk; q++) {
+      const double f = 2.0 * coef[q] * dks[q];
+      const double* xr = xs_tr + ((int64_t)q * npad + n) * d;
+      const double* xc = sx + (q * TILE + c) * ldx;
+#pragma unroll
+      for (int m = 0; m < MAXD; m++)
+        if (m < d) {
+          const double dk = f * (xc[m] - xr[m]) * hyp.invl[q][m];
+          gmu[m] = fma(an, dk, gmu[m]);
+          gs[m] = fma(wn_, dk, gs[m]);
+        }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MAXD; m++)
+    if (m < d) {
+      sred[((rg * TILE + c) * 2 + 0) * d + m] = gmu[m];
+      sred[((rg * TILE + c) * 2 + 1) * d + m] = gs[m];
+    }
+  __syncthreads();
+  if (tid >= TILE || mg >= M) return;
+  double mu = mu_io[mg], var = var_io[mg];
+  // outputs (om, ov) as functions of the latent (mu, var): partial derivatives a* = d om, b* = d ov
+  double am = 1.0, av = 0.0, bm = 0.0, bv = 1.0, cm = 0.0, cv = 0.0;   // c*: factor of d mean_add / d x
+  if (epi.mode != 0) {
+    const double madd = mean_add ? mean_add[mg] : 0.0;
+    const double sd = sqrt(2.0 * var);
+    double s1 = 0.0, s2 = 0.0, s1m = 0.0, s1v = 0.0, s2m = 0.0, s2v = 0.0, s1c = 0.0, s2c = 0.0;
+    for (int q = 0; q < epi.deg; q++) {
+      const double yi = sd * epi.nodes[q] + mu;
+      double dyr;
+      const double yr = prog_rev_const_d(epi.yrev, yi, dyr) + madd;
+      double f = yr, df = 1.0;
+      if (epi.mode == 2) {
+        const double dff = epi.ei_max ? (yr - epi.yopt) : (epi.yopt - yr);
+        f = dff > 0.0 ? dff : 0.0;
+        df = dff > 0.0 ? (epi.ei_max ? 1.0 : -1.0) : 0.0;
+      }
+      const double w = epi.weights[q];
+      const double dyv = dyr * epi.nodes[q] / sd;      // d yr / d var
+      s1 += w * f;
+      s2 += w * (yr * yr);
+      s1m += w * df * dyr;
+      s1v += w * df * dyv;
+      s1c += w * df;
+      s2m += w * 2.0 * yr * dyr;
+      s2v += w * 2.0 * yr * dyv;
+      s2c += w * 2.0 * yr;
+    }
+    const double ispi = 0.56418958354775628694807945156077;  // 1/sqrt(pi)
+    const double om = ispi * s1;
+    double ov = ispi * s2 - om * om;
+    am = ispi * s1m; av = ispi * s1v; cm = ispi * s1c;
+    bm = ispi * s2m - 2.0 * om * am;
+    bv = ispi * s2v - 2.0 * om * av;
+    cv = ispi * s2c - 2.0 * om * cm;
+    if (epi.normvar) {
+      const double i2 = 1.0 / (om * om), i3 = 2.0 * ov / (om * om * om);
+      bm = bm * i2 - i3 * am;
+      bv = bv * i2 - i3 * av;
+      cv = cv * i2 - i3 * cm;
+      ov *= i2;
+    }
+    mu = om;
+    var = ov;
+  }
+  mu_io[mg] = mu;
+  var_io[mg] = var;
+  for (int m = 0; m < d; m++) {
+    double g1 = 0.0, g2 = 0.0;
+    for (int r = 0; r < 4; r++) {
+      g1 += sred[((r * TILE + c) * 2 + 0) * d + m];
+      g2 += sred[((r * TILE + c) * 2 + 1) * d + m];
+    }
+    g2 *= -2.0;   // d var / d x_m
+    const double dm_add = dmean_add ? dmean_add[mg * d + m] : 0.0;
+    dmean_out[mg * d + m] = am * g1 + av * g2 + cm * dm_add;
+    dvar_out[mg * d + m] = bm * g1 + bv * g2 + cv * dm_add;
+  }
+}
+
 }  // namespace avn
 
 #include "kinv_fast.cuh"

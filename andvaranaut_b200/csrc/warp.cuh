@@ -195,6 +195,66 @@ __device__ __forceinline__ double prog_rev_const(const avn_warp_prog& pr, double
   return z;
 }
 
+// Frozen inverse of a single stage together with its derivative d rev / d z (chain rule of the BO refine graph,
+// gpmcmc.py:781-783: revmc inside a differentiated PyTensor expression).
+__device__ __forceinline__ double stage_rev_const_d(const avn_warp_stage& st, double z, double& dz) {
+  const double* p = st.c;
+  switch (st.op) {
+    case AVN_W_AFFINE_CONST:
+    case AVN_W_AFFINE:
+      dz = 1.0 / p[1];
+      return (z - p[0]) / p[1];
+    case AVN_W_LOG: {
+      const double e = exp(z);
+      dz = e;
+      return e;
+    }
+    case AVN_W_ARCSINH: {
+      const double u = (z - p[0]) / p[1];
+      dz = p[3] * cosh(u) / p[1];
+      return p[2] + p[3] * sinh(u);
+    }
+    case AVN_W_BOXCOX:
+    case AVN_W_BOXCOX_CONST: {
+      const double q = p[0] + 1.0;
+      const double t = z * q + 1.0;
+      const double sg = (t > 0.0) ? 1.0 : ((t < 0.0) ? -1.0 : 0.0);
+      dz = pow(fabs(t), 1.0 / q - 1.0);
+      return sg * pow(fabs(t), 1.0 / q);
+    }
+    case AVN_W_SINHARCSINH: {
+      const double u = (asinh(z) + p[0]) / p[1];
+      dz = cosh(u) / (p[1] * sqrt(1.0 + z * z));
+      return sinh(u);
+    }
+    case AVN_W_SAL: {
+      const double w = (z - p[2]) / p[3];
+      const double u = (asinh(w) + p[0]) / p[1];
+      dz = cosh(u) / (p[1] * p[3] * sqrt(1.0 + w * w));
+      return sinh(u);
+    }
+    case AVN_W_KUMARASWAMY: {
+      const double s = pow(1.0 - z, 1.0 / p[1]);
+      dz = (1.0 / p[0]) * pow(1.0 - s, 1.0 / p[0] - 1.0) * (1.0 / p[1]) * pow(1.0 - z, 1.0 / p[1] - 1.0);
+      return pow(1.0 - s, 1.0 / p[0]);
+    }
+    default:
+      dz = 1.0;
+      return z;
+  }
+}
+
+__device__ __forceinline__ double prog_rev_const_d(const avn_warp_prog& pr, double z, double& dz) {
+  double d = 1.0;
+  for (int s = pr.nstages - 1; s >= 0; s--) {
+    double ds;
+    z = stage_rev_const_d(pr.st[s], z, ds);
+    d *= ds;
+  }
+  dz = d;
+  return z;
+}
+
 // Run one composite warp over a strided column of N values, in place.
 //   val[n*vstride]                 running value (in: raw data, out: converted)
 //   dual[n*dstride + q], q < np    d value / d param_q (zeroed here)

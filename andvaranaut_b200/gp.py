@@ -273,3 +273,33 @@ class GPEngine:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         return mean, var
+
+    def predict_grad(self, Xs, epilogue=None, mean_add=None, dmean_add=None, pred_noise=True, max_ws_bytes=4 << 30):
+        """Xs [M,nx] converted query points -> (mean [M], var [M], dmean [M,nx], dvar [M,nx]) device tensors: the
+        predictive graph of the BO refine step (gpmcmc.py:738-801) with its gradient w.r.t. the query points.
+        ``pred_noise=False`` leaves ``gv`` out of the variance as that inline graph does."""
+        if self._state is None:
+            raise GPError('factorize first')
+        Xs = self._dev(Xs)
+        if Xs.ndim != 2 or Xs.shape[1] != self.nx:
+            raise ValueError('Xs must be [M,nx]')
+        M = Xs.shape[0]
+        epi = epilogue if epilogue is not None else self.make_epilogue()
+        need = min(self.lib.avn_gp_predict_grad_workspace_bytes(self._h, M), max_ws_bytes)
+        need = max(need, 2 * self.npad * 64 * 8)
+        if self._pws is None or self._pws.numel() < need:
+            self._pws = None
+            self._pws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        mean = torch.empty(M, dtype=torch.float64, device=self.device)
+        var = torch.empty(M, dtype=torch.float64, device=self.device)
+        dmean = torch.empty(M, self.nx, dtype=torch.float64, device=self.device)
+        dvar = torch.empty(M, self.nx, dtype=torch.float64, device=self.device)
+        madd = self._dev(mean_add).reshape(-1) if mean_add is not None else None
+        dmadd = self._dev(dmean_add).reshape(M, self.nx) if dmean_add is not None else None
+        rc = self.lib.avn_gp_predict_grad(self._h, _ptr(self._state), _ptr(Xs), M, C.byref(epi), 1 if pred_noise else 0,
+                                          _ptr(madd), _ptr(dmadd), _ptr(mean), _ptr(var), _ptr(dmean), _ptr(dvar),
+                                          _ptr(self._pws), self._pws.numel(), _stream())
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        return mean, var, dmean, dvar

@@ -13,7 +13,8 @@ Replaced: the PyMC model (``self.m``) is a :class:`~andvaranaut_b200.priors.Para
 per-point Python loop ``__gh_stats`` (:545-569) are one device call.  Documented deviations: ``seed`` is
 honoured by ``sample``; ``restarts > 1`` really restarts from different (prior-drawn) points (the reference
 builds a start and never passes it on, :330-332); the BO ``refine`` step polishes the candidate with bounded
-L-BFGS-B on the same acquisition (finite differences through batched predict) instead of a PyMC model over x.
+L-BFGS-B on the reference's own inline acquisition graph (:738-829) evaluated on the device with its analytic
+gradient w.r.t. the query point (:meth:`GPMCMC.acquisition_grad`) instead of a PyMC model over x.
 """
 import copy
 import re
@@ -515,7 +516,9 @@ class GPMCMC(LHC):
                     if self.verbose:
                         print(f'Function opt is {np.min(ys):0.3f}')
                 if refine and opt_method in ('predict', 'map'):
-                    xsamp = self.__refine(optf, xsamp, lbs, ubs)
+                    xsamp = self.__refine(optf, xsamp, lbs, ubs,
+                                          acq=lambda xx: self.acquisition_grad(xx, method=method, opt_type=opt_type,
+                                                                               normvar=normvar, jitter=jitter))
             else:
                 xsamp = np.array([[p.rvs(random_state=rng) for p in self.priors]])
             xdiff = np.sum(np.abs(xsamp - xsampold) / np.abs(xsampold)) / self.nx
@@ -546,9 +549,75 @@ class GPMCMC(LHC):
                 self.fit(method=fit_method, iwgp=iwgp, cwgp=cwgp, jitter=jitter, **kwargs)
         return self.xopt, self.yopt
 
-    def __refine(self, optf, xsamp, lbs, ubs):
-        """bounded L-BFGS-B polish of one candidate; each gradient is ONE batched predict of 2 nx + 1 points."""
+    def _con_with_der(self, x):
+        """converted inputs and d con / d x per column (analytic ``der`` where the conrev class has one, central
+        differences of ``con`` otherwise)."""
+        xc, dc = np.empty_like(x), np.empty_like(x)
+        for i in range(self.nx):
+            c = self.xconrevs[i]
+            xc[:, i] = c.con(x[:, i])
+            if isinstance(c, _none_conrev):
+                dc[:, i] = 1.0
+            elif hasattr(c, 'der'):
+                dc[:, i] = c.der(x[:, i])
+            else:
+                h = 1e-6 * np.maximum(1.0, np.abs(x[:, i]))
+                dc[:, i] = (c.con(x[:, i] + h) - c.con(x[:, i] - h)) / (2 * h)
+        return xc, dc
+
+    def acquisition_grad(self, x, method='EI', opt_type='min', normvar=True, jitter=1e-6, deg=8):
+        """Value and gradient w.r.t. the raw query points x [M,nx] of the acquisition the reference builds inline
+        for its BO refine / ``opt_method='map'`` step (gpmcmc.py:738-829) and differentiates with PyTensor: the
+        reverted predictive mean (exploit / eps-RS), the reverted variance WITHOUT the noise term (explore) or the
+        expected improvement (EI), signed so that SMALLER is better.  One device call for all M points.
+        Returns (f [M], g [M,nx]), or None when the output transform has no device program."""
+        from .gp import GPEngine
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        progs = _frozen_programs(self.yconrevs[0])
+        if progs is None:
+            return None
+        eng, _ = self._predict_engine(jitter)
+        xc, dc = self._con_with_der(x)
+        madd = dmadd = None
+        if self.mean != self.zero_mean:
+            madd = self.__mean_values(x)[:, 0]
+            dmadd = np.empty_like(x)
+            for i in range(self.nx):       # user mean function: central differences on the host
+                h = np.zeros(self.nx)
+                h[i] = 1e-6 * max(1.0, float(np.max(np.abs(x[:, i]))))
+                dmadd[:, i] = (self.__mean_values(x + h)[:, 0] - self.__mean_values(x - h)[:, 0]) / (2 * h[i])
+            dmadd = dmadd / dc             # the device differentiates w.r.t. the converted inputs
+        epi = GPEngine.make_epilogue(mode='EI' if method == 'EI' else 'revert', deg=deg,
+                                     normvar=normvar and method == 'explore', EIopt=opt_type,
+                                     yopt=0.0 if self.yopt is None else float(self.yopt), yrev=progs[1])
+        m, v, dm, dv = (t.cpu().numpy() for t in eng.predict_grad(xc, epilogue=epi, mean_add=madd, dmean_add=dmadd,
+                                                                  pred_noise=False))
+        if method in ('eps-RS', 'exploit'):
+            sgn = 1.0 if opt_type == 'min' else -1.0
+            return sgn * m, sgn * dm * dc
+        if method == 'explore':
+            return -v, -dv * dc
+        return -m, -dm * dc
+
+    def __refine(self, optf, xsamp, lbs, ubs, acq=None):
+        """bounded L-BFGS-B polish of one candidate.  With ``acq`` (see :meth:`acquisition_grad`) every step is one
+        device call returning value and analytic gradient; otherwise each gradient is ONE batched predict of
+        2 nx + 1 points (central differences)."""
         from scipy.optimize import minimize
+        if acq is not None:
+            try:
+                if acq(xsamp) is not None:
+                    def fa(x):
+                        f, g = acq(x[None, :])
+                        return float(f[0]), g[0]
+                    f0 = fa(xsamp[0])[0]
+                    res = minimize(fa, xsamp[0], jac=True, method='L-BFGS-B', bounds=list(zip(lbs, ubs)),
+                                   options=dict(maxiter=50))
+                    if np.isfinite(res.fun) and res.fun <= f0:
+                        return np.array([res.x])
+                    return xsamp
+            except Exception:
+                pass
         span = ubs - lbs
 
         def fg(x):

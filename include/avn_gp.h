@@ -134,6 +134,17 @@ int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* Xs_dev, int6
                    const double* mean_add_dev, double* out_mean_dev, double* out_var_dev, void* ws_dev,
                    size_t ws_bytes, void* stream);
 
+/* BO refine (gpmcmc.py:738-801): the predictive graph the reference differentiates w.r.t. the query point inside
+ * pm.find_MAP -- here value AND analytic gradient for M query points at once.  Same epilogue as avn_gp_predict;
+ * pred_noise = 0 leaves gv out of the variance as that inline graph does (:775-778), 1 matches gp.predict(pred_noise=True).
+ * dmean_add [M,d] = gradient of the user mean function w.r.t. the converted inputs, or NULL.
+ * out_dmean / out_dvar [M,d]: d out_mean / d Xs, d out_var / d Xs (converted-input space; the caller chains d con / d x). */
+size_t avn_gp_predict_grad_workspace_bytes(const avn_gp* gp, int64_t M);
+int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const double* Xs_dev, int64_t M, const avn_epilogue* epi,
+                        int32_t pred_noise, const double* mean_add_dev, const double* dmean_add_dev,
+                        double* out_mean_dev, double* out_var_dev, double* out_dmean_dev, double* out_dvar_dev,
+                        void* ws_dev, size_t ws_bytes, void* stream);
+
 /* introspection used by bench.py: number of kernel launches issued by the last call on this handle */
 int64_t avn_gp_last_launch_count(const avn_gp* gp);
 

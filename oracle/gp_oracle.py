@@ -359,6 +359,78 @@ def predict_blocked(spec, theta, Xc, z, Xs, block=4096, L=None):
     return mu, var, L
 
 
+def predict_grad(spec: ModelSpec, theta, Xc, z, Xs, pred_noise=True):
+    """Latent mean / variance and their gradients w.r.t. the converted query points Xs [M,nx]: the expression the
+    reference builds inline for the BO refine step and hands to PyTensor autodiff (gpmcmc.py:738-778: kstar,
+    v = solve_triangular(L, kstar), ycpmean = kstar^T alpha, ycpvar = k** - v^T v; note: no ``+ gv`` there, i.e.
+    ``pred_noise=False``).  Closed forms of the same derivatives:
+        d mu / d x = sum_i alpha_i dk_i/dx,   d var / d x = -2 sum_i (K^-1 k*)_i dk_i/dx,
+        dk_i/dx_m = sum_q coef_q kv_q k_q'(r2_q) * 2 (x_m - X_im) / l_qm^2   (zero where square_dist was clipped).
+    Returns (mu [M], var [M], dmu [M,nx], dvar [M,nx])."""
+    th = unpack(spec, theta)
+    N, M = Xc.shape[0], Xs.shape[0]
+    Kxx = cov_matrix(spec, th, Xc)
+    sig2 = np.square(np.sqrt(th['gv']))
+    L = sla.cholesky((Kxx + spec.jitter * np.eye(N)) + np.eye(N) * sig2, lower=True, check_finite=False)
+    Kxs, coef, parts = cov_matrix(spec, th, Xc, Xs, want_parts=True)
+    A = sla.solve_triangular(L, Kxs, lower=True, check_finite=False)
+    v = sla.solve_triangular(L, z, lower=True, check_finite=False)
+    alpha = sla.solve_triangular(L.T, v, lower=False, check_finite=False)
+    Wm = sla.solve_triangular(L.T, A, lower=False, check_finite=False)      # K^-1 K_xs  [N,M]
+    mu = np.dot(A.T, v)
+    var = kdiag_total(spec, th['kv']) - np.sum(np.square(A), 0)
+    if pred_noise:
+        var = var + sig2
+    dmu = np.zeros((M, spec.nx))
+    dvar = np.zeros((M, spec.nx))
+    for k in range(spec.nkern):
+        r2, kk, dk = parts[k]
+        ls = th['l'][k * spec.nx:(k + 1) * spec.nx]
+        F = coef[k] * th['kv'][k] * dk * (r2 > 0.0)                          # [N,M]
+        for m in range(spec.nx):
+            D = (Xs[:, m][None, :] - Xc[:, m][:, None]) * (2.0 / ls[m] ** 2)  # d r2 / d x_m
+            dmu[:, m] += np.sum(alpha[:, None] * F * D, axis=0)
+            dvar[:, m] += -2.0 * np.sum(Wm * F * D, axis=0)
+    return mu, var, dmu, dvar
+
+
+def gh_stats_grad(mu, var, dmu, dvar, rev, der, mean_add=None, dmean_add=None, normvar=True, deg=8, EI=False,
+                  EIopt=None, yopt=None):
+    """:func:`gh_stats` together with the gradient of both outputs w.r.t. the query points, given the gradients of
+    the latent mean / variance (chain rule of gpmcmc.py:780-801).  ``rev`` is the frozen output reversion, ``der``
+    the derivative of its forward map (``d con / d y``), so ``d rev / d z = 1 / der(rev(z))``."""
+    xi, wi = np.polynomial.hermite.hermgauss(deg)
+    mu = np.asarray(mu, dtype=np.float64).reshape(-1)
+    var = np.asarray(var, dtype=np.float64).reshape(-1)
+    sd = np.sqrt(2 * var)
+    yi = sd[:, None] * xi[None, :] + mu[:, None]
+    y0 = rev(yi)
+    dyr = 1.0 / der(y0)
+    yir = y0 if mean_add is None else y0 + np.asarray(mean_add).reshape(-1, 1)
+    dyv = dyr * xi[None, :] / sd[:, None]
+    if EI:
+        dff = yir - yopt if EIopt == 'max' else yopt - yir
+        f = np.where(dff > 0.0, dff, 0.0)
+        df = np.where(dff > 0.0, 1.0 if EIopt == 'max' else -1.0, 0.0)
+    else:
+        f, df = yir, np.ones_like(yir)
+    c = 1 / np.sqrt(np.pi)
+    m = c * np.sum(wi * f, axis=1)
+    m2 = c * np.sum(wi * yir ** 2, axis=1)
+    v = m2 - m ** 2
+    am, av, cm = c * np.sum(wi * df * dyr, axis=1), c * np.sum(wi * df * dyv, axis=1), c * np.sum(wi * df, axis=1)
+    bm = c * np.sum(wi * 2 * yir * dyr, axis=1) - 2 * m * am
+    bv = c * np.sum(wi * 2 * yir * dyv, axis=1) - 2 * m * av
+    cv = c * np.sum(wi * 2 * yir, axis=1) - 2 * m * cm
+    if normvar:
+        bm, bv, cv = (b / m ** 2 - 2 * v * a / m ** 3 for a, b in ((am, bm), (av, bv), (cm, cv)))
+        v = v / m ** 2
+    dma = np.zeros_like(dmu) if dmean_add is None else np.asarray(dmean_add)
+    dm_out = am[:, None] * dmu + av[:, None] * dvar + cm[:, None] * dma
+    dv_out = bm[:, None] * dmu + bv[:, None] * dvar + cv[:, None] * dma
+    return m, v, dm_out, dv_out
+
+
 def gh_stats_loop(mu, var, rev, mean_add=None, normvar=True, deg=8, EI=False, EIopt=None, yopt=None):
     """Literal restatement of GPMCMC.__gh_stats (gpmcmc.py:545-569): per-point Python loop."""
     xi, wi = np.polynomial.hermite.hermgauss(deg)

@@ -153,3 +153,47 @@ def test_predict_with_mean_function_and_user_transform(tmp_path):
     g.fit()
     y = g.predict(g.x[:8])
     assert np.max(np.abs(y[:, 0] - g.y[:8, 0])) < 0.05
+
+
+@pytest.mark.parametrize('method,opt_type', [('EI', 'min'), ('EI', 'max'), ('exploit', 'min'), ('explore', 'min')])
+def test_acquisition_grad_matches_oracle_graph(tmp_path, method, opt_type):
+    """the BO refine graph (gpmcmc.py:738-829): value against the oracle's restatement of it (variance WITHOUT gv,
+    GH reversion, EI), gradient w.r.t. the RAW query point against central differences of that oracle value."""
+    g = GPMCMC(kernel='Matern52', noise=True, xconrevs=[uniform(SPACE[0]), normal(SPACE[1])],
+               yconrevs=[None], mean=lambda x: np.array([0.1 * x[0]]),
+               nx=2, ny=1, priors=SPACE, target=lambda x: target_fun(x) + 3.0, verbose=False, rundir=str(tmp_path / 'runs'))
+    g.sample(40, seed=7)
+    g.change_yconrevs([wgp(['logarithm', 'sal', 'meanstd'], [0.0, 1.0, 0.0, 1.0], y=(g.y - g.ym)[:, 0])])
+    g.fit(cwgp=True)
+    g.yopt = float(np.min(g.y)) if opt_type == 'min' else float(np.max(g.y))
+    spec = go.ModelSpec(nx=2, kerns=['Matern52'], noise=True)
+    sp = ParamSpace(2, 1, True)
+    th = sp.theta_from_hypers(g.hypers)
+    w = g.yconrevs[0]
+
+    def oracle_value(x):
+        xc = np.column_stack([g.xconrevs[i].con(x[:, i]) for i in range(2)])
+        mu, var = go.predict(spec, th, g.xc, g.yc[:, 0], xc)
+        var = var - go.unpack(spec, th)['gv']
+        madd = 0.1 * x[:, 0]
+        m, v = go.gh_stats(mu, var, w.rev, mean_add=madd, normvar=(method == 'explore'), EI=(method == 'EI'),
+                           EIopt=opt_type, yopt=g.yopt)
+        if method == 'explore':
+            return -v[:, 0]
+        if method == 'EI':
+            return -m[:, 0]
+        return m[:, 0] if opt_type == 'min' else -m[:, 0]
+
+    rng = np.random.default_rng(5)
+    x = np.column_stack([rng.uniform(0.1, 1.9, 12), rng.uniform(1.05, 1.45, 12)])
+    f, gr = g.acquisition_grad(x, method=method, opt_type=opt_type, normvar=True)
+    ref = oracle_value(x)
+    assert np.max(np.abs(f - ref)) <= 1e-8 * np.max(np.abs(ref))
+    # the normalised variance is ~1e-6 and a cancelling difference (kv - |v|^2): its central differences carry
+    # ~1e-10 / h of rounding noise, hence the wider step and tolerance for 'explore'
+    hh, tol = (1e-5, 1e-3) if method == 'explore' else (1e-6, 2e-5)
+    for i in range(2):
+        h = np.zeros(2)
+        h[i] = hh
+        fd = (oracle_value(x + h) - oracle_value(x - h)) / (2 * hh)
+        assert np.max(np.abs(gr[:, i] - fd)) <= tol * max(np.max(np.abs(fd)), np.max(np.abs(gr))), (i, gr[:, i], fd)

@@ -303,3 +303,64 @@ def test_full_size_properties_config4():
     a = eng.predict(Xs)
     b = eng.predict(Xs, max_ws_bytes=eng.npad * 64 * 8 * 5)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ---- BO refine graph (gpmcmc.py:738-801): predictive mean / variance / EI with gradients w.r.t. the query ----
+@pytest.mark.parametrize('name,N,M', [('rbf', 100, 5), ('m52', 200, 130), ('m32', 70, 64), ('expo', 90, 3),
+                                      ('rq', 130, 20), ('sum', 150, 77), ('mix3', 100, 10), ('rqprod', 65, 1)])
+def test_predict_grad_latent(name, N, M):
+    from test_oracle import SPECS
+    spec = SPECS[name]
+    X, y, th, Xs = cases.synth(spec, N, seed=31, M=M)
+    eng = engine(spec)
+    eng.set_data(X, y)
+    eng.factorize(th)
+    for pn in (True, False):
+        rm, rv, rdm, rdv = go.predict_grad(spec, th, X, y, Xs, pred_noise=pn)
+        m, v, dm, dv = (t.cpu().numpy() for t in eng.predict_grad(Xs, pred_noise=pn))
+        kv = float(np.max(go.unpack(spec, th)['kv']))
+        assert np.max(np.abs(m - rm)) <= 1e-8 * np.max(np.abs(rm))
+        assert np.max(np.abs(v - rv)) <= 1e-8 * max(np.max(np.abs(rv)), kv)
+        # gradients are sums of N cancelling terms: compared relative to the largest component
+        assert np.max(np.abs(dm - rdm)) <= 1e-8 * np.max(np.abs(rdm)), name
+        tol = 1e-6 if name == 'expo' else 1e-8   # Exponential: dk/dr2 ~ 1/r, see the module docstring of test_oracle
+        assert np.max(np.abs(dv - rdv)) <= tol * max(np.max(np.abs(rdv)), kv), name
+    # same values as the plain predict path
+    m0, v0 = eng.predict(Xs)
+    assert torch.allclose(m0, eng.predict_grad(Xs)[0], rtol=1e-12, atol=1e-14)
+
+
+def test_predict_grad_epilogues():
+    from andvaranaut_b200 import transform as T
+    from andvaranaut_b200.gp import GPEngine
+    spec = go.ModelSpec(nx=3, kerns=['Matern52'])
+    rng = np.random.default_rng(13)
+    X, yraw, th, Xs = cases.synth(go.ModelSpec(nx=3, kerns=['Matern52'], ywarp=['logarithm']), 150, seed=5, M=100)
+    th = th[:5]
+    madd, dmadd = rng.normal(size=len(Xs)) * 0.1, rng.normal(size=Xs.shape) * 0.1
+    yopt = float(np.min(yraw))
+    for stages, params in [(['logarithm', 'sal', 'meanstd'], [0.1, 1.1, -0.2, 0.9]),
+                           (['affine', 'arcsinh', 'boxcox', 'sinharcsinh', 'meanstd'],
+                            [0.1, 1.2, 0.1, 1.1, -0.1, 0.9, 0.3, 0.05, 1.05]),
+                           (['meanstd'], [])]:
+        w = T.wgp(stages, params, y=yraw)
+        z = w.con(yraw)
+        eng = engine(spec)
+        eng.set_data(X, z)
+        eng.factorize(th)
+        for pn in (True, False):
+            lat = go.predict_grad(spec, th, X, z, Xs, pred_noise=pn)
+            for kw, ekw in [
+                (dict(normvar=False), dict(mode='revert', normvar=False)),
+                (dict(normvar=True), dict(mode='revert', normvar=True)),
+                (dict(EI=True, EIopt='min', yopt=yopt, normvar=False), dict(mode='EI', EIopt='min', yopt=yopt)),
+                (dict(EI=True, EIopt='max', yopt=yopt, normvar=False), dict(mode='EI', EIopt='max', yopt=yopt)),
+            ]:
+                rm, rv, rdm, rdv = go.gh_stats_grad(*lat, w.rev, w.der, mean_add=madd, dmean_add=dmadd, **kw)
+                epi = GPEngine.make_epilogue(yrev=w.rev_program(), **ekw)
+                m, v, dm, dv = (t.cpu().numpy() for t in eng.predict_grad(Xs, epilogue=epi, mean_add=madd,
+                                                                          dmean_add=dmadd, pred_noise=pn))
+                assert np.max(np.abs(m - rm)) <= 1e-8 * np.max(np.abs(rm)), (stages, kw)
+                assert np.max(np.abs(v - rv)) <= 1e-8 * max(np.max(np.abs(rv)), np.max(rm ** 2)), (stages, kw)
+                assert np.max(np.abs(dm - rdm)) <= 1e-8 * np.max(np.abs(rdm)), (stages, kw)
+                assert np.max(np.abs(dv - rdv)) <= 1e-7 * max(np.max(np.abs(rdv)), np.max(np.abs(rdm))), (stages, kw)

@@ -215,3 +215,43 @@ def test_oracle_matches_scikit_learn_gp(kern, tol):
     mu, var = go.predict(spec, th, X, y, Xs)
     assert np.max(np.abs(mu - mu_sk)) <= 1e-7 * np.max(np.abs(mu_sk))
     assert np.max(np.abs(var - sd_sk ** 2) / np.maximum(sd_sk ** 2, p['kv'][0])) <= 1e-7
+
+
+# ---- BO refine graph: gradients of the predictive mean / variance w.r.t. the query points -------------------
+@pytest.mark.parametrize('name', ['rbf', 'm52', 'm32', 'rq', 'sum', 'mix3', 'rqprod'])
+def test_oracle_predict_grad_vs_finite_differences(name):
+    spec = SPECS[name]
+    X, y, th, Xs = cases.synth(spec, 40, seed=21, M=6)
+    for pn in (True, False):
+        mu, var, dmu, dvar = go.predict_grad(spec, th, X, y, Xs, pred_noise=pn)
+        mu0, var0 = go.predict(spec, th, X, y, Xs)
+        gv = go.unpack(spec, th)['gv']
+        assert np.allclose(mu, mu0, rtol=1e-12) and np.allclose(var, var0 - (0.0 if pn else gv), rtol=1e-10, atol=1e-13)
+    h = 1e-6
+    for m in range(spec.nx):
+        e = np.zeros(spec.nx)
+        e[m] = h
+        mp, vp = go.predict(spec, th, X, y, Xs + e)
+        mm, vm = go.predict(spec, th, X, y, Xs - e)
+        assert np.allclose((mp - mm) / (2 * h), dmu[:, m], rtol=2e-6, atol=2e-6 * np.max(np.abs(dmu)))
+        assert np.allclose((vp - vm) / (2 * h), dvar[:, m], rtol=2e-6, atol=2e-6 * np.max(np.abs(dvar)))
+
+
+def test_oracle_gh_stats_grad_vs_finite_differences():
+    rng = np.random.default_rng(4)
+    M, d = 9, 3
+    mu, var = rng.normal(size=M) * 0.5, rng.uniform(0.02, 0.4, M)
+    dmu, dvar = rng.normal(size=(M, d)), 0.1 * rng.normal(size=(M, d))
+    w = T.wgp(['logarithm', 'sal', 'meanstd'], [0.1, 1.1, -0.2, 0.9], y=np.exp(rng.normal(size=40)))
+    madd, dmadd = rng.normal(size=M) * 0.1, rng.normal(size=(M, d)) * 0.1
+    h = 1e-6
+    for kw in [dict(normvar=False), dict(normvar=True), dict(EI=True, EIopt='max', yopt=0.7, normvar=False),
+               dict(EI=True, EIopt='min', yopt=1.5, normvar=False)]:
+        m, v, dm, dv = go.gh_stats_grad(mu, var, dmu, dvar, w.rev, w.der, mean_add=madd, dmean_add=dmadd, **kw)
+        m0, v0 = go.gh_stats(mu, var, w.rev, mean_add=madd, **kw)
+        assert np.allclose(m, m0[:, 0], rtol=1e-13) and np.allclose(v, v0[:, 0], rtol=1e-11, atol=1e-13)
+        for k in range(d):   # move along direction k: latent mean / variance / mean function to first order
+            a = go.gh_stats(mu + h * dmu[:, k], var + h * dvar[:, k], w.rev, mean_add=madd + h * dmadd[:, k], **kw)
+            b = go.gh_stats(mu - h * dmu[:, k], var - h * dvar[:, k], w.rev, mean_add=madd - h * dmadd[:, k], **kw)
+            assert np.allclose((a[0] - b[0])[:, 0] / (2 * h), dm[:, k], rtol=1e-6, atol=1e-7 * np.max(np.abs(dm))), kw
+            assert np.allclose((a[1] - b[1])[:, 0] / (2 * h), dv[:, k], rtol=1e-6, atol=1e-7 * np.max(np.abs(dv))), kw
