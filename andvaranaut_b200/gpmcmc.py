@@ -26,6 +26,7 @@ from . import transform as T
 from .drivers import Posterior, find_map, find_map_multi, sample as hmc_sample
 from .lhc import LHC
 from .priors import ParamSpace
+from .xpost import InverseLikelihood, XPosterior, kdiag_values
 from .transform import wgp
 
 __all__ = ['GPMCMC']
@@ -292,7 +293,7 @@ class GPMCMC(LHC):
                 raise Exception("Error: method='none' needs previously fitted hypers")
         elif method in ('mcmc_mean', 'mcmc_map'):
             skw = {k: kwargs.pop(k) for k in ('draws', 'tune', 'chains', 'seed', 'target_accept', 'max_leapfrog',
-                                              'path_length', 'init_jitter') if k in kwargs}
+                                              'path_length', 'init_jitter', 'sampler', 'max_treedepth') if k in kwargs}
             skw.setdefault('chains', 4)
             kwargs.pop('cores', None)
             kwargs.pop('random_seed', None)
@@ -509,13 +510,17 @@ class GPMCMC(LHC):
                     res = differential_evolution(optf, list(zip(lbs, ubs)), vectorized=True, updating='deferred',
                                                  seed=int(rng.integers(2 ** 31)))
                     xsamp = np.array([res.x])
+                elif opt_method in ('map', 'mcmc_mean', 'mcmc_map'):
+                    xsamp = self.__acquisition_model_opt(opt_method, method, opt_type, normvar, jitter, rng, **kwargs)
+                elif opt_method != 'predict':
+                    raise Exception('opt_method must be one of map, mcmc_map, or mcmc_mean')
                 else:
                     xs = self._LHC__latin_sample(predict_samps, seed=int(rng.integers(2 ** 31)))
                     ys = optf(xs)
                     xsamp = np.array([xs[int(np.argmin(ys)), :]])
                     if self.verbose:
                         print(f'Function opt is {np.min(ys):0.3f}')
-                if refine and opt_method in ('predict', 'map'):
+                if refine and opt_method == 'predict':
                     xsamp = self.__refine(optf, xsamp, lbs, ubs,
                                           acq=lambda xx: self.acquisition_grad(xx, method=method, opt_type=opt_type,
                                                                                normvar=normvar, jitter=jitter))
@@ -599,22 +604,68 @@ class GPMCMC(LHC):
             return -v, -dv * dc
         return -m, -dm * dc
 
+    def _acquisition_posterior(self, method, opt_type, normvar, jitter):
+        """the PyMC model the reference rebuilds every BO iteration (gpmcmc.py:699-824): x priors + Potential(acquisition)."""
+        def potential(x):
+            f, g = self.acquisition_grad(x, method=method, opt_type=opt_type, normvar=normvar, jitter=jitter)
+            return -f, -g
+        return XPosterior(self.priors, potential)
+
+    def __x_model_opt(self, post, opt_method, rng, **kwargs):
+        """MAP (random start, gpmcmc.py:831-832 / :1169-1170) or MCMC (:844-853 / :1175-1188) over the x model."""
+        maxeval = kwargs.pop('maxeval', 5000)
+        kwargs.pop('progressbar', None)
+        if opt_method == 'map':
+            restarts = int(kwargs.pop('restarts', 1))
+            kwargs.pop('seed', None)
+            z0 = rng.standard_normal((restarts, post.space.P))
+            zs, lps = find_map_multi(post, z0, maxeval=maxeval, **kwargs)
+            lps = np.where(np.isfinite(lps), lps, -np.inf)
+            mp = post.space.hypers_dict(zs[int(np.argmax(lps))])
+            return mp, mp
+        if opt_method not in ('mcmc_mean', 'mcmc_map'):
+            raise Exception('method must be one of map, mcmc_map, or mcmc_mean')
+        skw = {k: kwargs.pop(k) for k in ('draws', 'tune', 'chains', 'seed', 'target_accept', 'max_leapfrog',
+                                          'path_length', 'init_jitter', 'sampler', 'max_treedepth') if k in kwargs}
+        skw.setdefault('chains', 4)
+        skw.setdefault('seed', int(rng.integers(2 ** 31)))
+        data = hmc_sample(post, **skw)
+        if opt_method == 'mcmc_mean':
+            mp = self.mean_extract(data)
+        else:
+            mp = self.map_extract(data)
+            try:
+                z, _, _ = find_map(post, post.space.initial_z(mp), maxeval=maxeval)
+                mp = post.space.hypers_dict(z)
+            except Exception:
+                pass
+        return data, mp
+
+    def __acquisition_model_opt(self, opt_method, method, opt_type, normvar, jitter, rng, **kwargs):
+        if _frozen_programs(self.yconrevs[0]) is None:
+            raise Exception('Error: the output transform has no device program; use opt_method="predict" or "DE"')
+        post = self._acquisition_posterior(method, opt_type, normvar, jitter)
+        _, mp = self.__x_model_opt(post, opt_method, rng, **kwargs)
+        return np.array([[float(mp[f'x{j}']) for j in range(self.nx)]])
+
     def __refine(self, optf, xsamp, lbs, ubs, acq=None):
-        """bounded L-BFGS-B polish of one candidate.  With ``acq`` (see :meth:`acquisition_grad`) every step is one
-        device call returning value and analytic gradient; otherwise each gradient is ONE batched predict of
-        2 nx + 1 points (central differences)."""
+        """polish of one candidate.  With ``acq`` (see :meth:`acquisition_grad`) this is the reference's own refine
+        step -- find_MAP of the x model started at the candidate (gpmcmc.py:833-837) -- every evaluation one device
+        call returning value and analytic gradient; otherwise bounded L-BFGS-B where each gradient is ONE batched
+        predict of 2 nx + 1 points (central differences)."""
         from scipy.optimize import minimize
         if acq is not None:
             try:
                 if acq(xsamp) is not None:
-                    def fa(x):
-                        f, g = acq(x[None, :])
-                        return float(f[0]), g[0]
-                    f0 = fa(xsamp[0])[0]
-                    res = minimize(fa, xsamp[0], jac=True, method='L-BFGS-B', bounds=list(zip(lbs, ubs)),
-                                   options=dict(maxiter=50))
-                    if np.isfinite(res.fun) and res.fun <= f0:
-                        return np.array([res.x])
+                    def potential(x):
+                        f, g = acq(x)
+                        return -f, -g
+                    post = XPosterior(self.priors, potential)
+                    z0 = post.space.z_from_theta(np.clip(xsamp[0], lbs, ubs))
+                    f0 = post.logp_dlogp(z0[None, :], False)[0][0]
+                    z, f1, _ = find_map(post, z0, maxeval=200)
+                    if np.isfinite(f1) and f1 >= f0:
+                        return post.space.theta_from_z(z[None, :])[0]
                     return xsamp
             except Exception:
                 pass
@@ -635,3 +686,79 @@ class GPMCMC(LHC):
         except Exception:
             pass
         return xsamp
+
+    # ---- Bayesian inverse problem --------------------------------------------------------------------
+    def __gh_stats_inv(self, y, yv, deg=8):
+        """variance of the converted observation by Gauss-Hermite quadrature (gpmcmc.py:573-585); as in the
+        reference the value of the LAST observation is returned (its loop overwrites the result)."""
+        xi, wi = np.polynomial.hermite.hermgauss(deg)
+        yi = np.sqrt(2 * yv[-1, 0]) * xi + y[-1, 0]
+        yir = self.yconrevs[0].con(yi)
+        ym = np.sum(wi * yir) / np.sqrt(np.pi)
+        return np.sum(wi * np.power(yir, 2)) / np.sqrt(np.pi) - ym ** 2
+
+    def inverse_posterior(self, yobs, yvarobs=None, jitter=1e-6):
+        """log posterior over the unknown input point given observations ``yobs`` [nobs,1] (optionally with
+        variances ``yvarobs`` [nobs,1]): the model of gpmcmc.py:1049-1165 as an :class:`XPosterior`.  Replicated
+        quirks: square roots of the variances go on the diagonal (:1138-1149); without ``yvarobs``
+        the observation rows get no noise at all; the mean function is not subtracted from ``yobs`` (:1134);
+        ``yder`` is taken at the raw outputs (:1152-1153)."""
+        from .gp import GPEngine
+        if self.hypers is None:
+            raise Exception('Model must be fitted before running Bayesian optimisation')
+        yobs = np.asarray(yobs, dtype=np.float64).reshape(-1, 1)
+        nobs = len(yobs)
+        yo_c = self.yconrevs[0].con(yobs[:, 0])
+        noise_t = np.sqrt(self.hypers['gv'] + jitter) if self.noise else np.sqrt(jitter)
+        noise_o = 0.0
+        if yvarobs is not None:
+            noise_o = np.sqrt(self.__gh_stats_inv(yobs, np.asarray(yvarobs, dtype=np.float64).reshape(-1, 1)))
+        if nobs > 1 and not noise_o > 0.0:
+            raise Exception('Error: several observations of one point need yvarobs (singular covariance otherwise)')
+        # A = K_tt + noise_t I : an engine with a noise term and no jitter, "gv" = the value the reference adds
+        eng = GPEngine(nx=self.nx, kerns=self.kerns, ops=self.ops, noise=True, jitter=0.0, device=self.device)
+        eng.set_data(self.xc, self.yc[:, 0])
+        space = ParamSpace(self.nx, self.nkern, True, has_alpha='RatQuad' in self.kerns)
+        hyp = dict(self.hypers)
+        hyp['gv'] = float(noise_t)
+        th = space.theta_from_hypers(hyp)
+        ll, _, info = eng.loglik_grad(th, want_grad=False)
+        if int(info[0]) != 0 or int(eng.factorize(th)[0]) != 0:
+            raise Exception('Error: covariance matrix not positive definite')
+        c = self.yconrevs[0]
+        yfull = np.r_[self.y[:, 0], yobs[:, 0]]
+        lyder = 0.0 if isinstance(c, _none_conrev) else float(np.sum(np.log(c.der(yfull))))
+        cfull, cdiag = kdiag_values(self.kerns, self.ops, self.hypers['kv'], float(self.hypers.get('alpha', 1.0)))
+        pot = InverseLikelihood(eng, self._con_with_der, yo_c, noise_o, cfull - cdiag, float(ll[0]) + lyder)
+        return XPosterior(self.priors, pot)
+
+    def inverse_opt(self, yobs, yvarobs=None, method='map', evaluate_opt=False, jitter=1e-6, seed=None, **kwargs):
+        """Bayesian inverse solver (gpmcmc.py:1040-1217): the input point that explains ``yobs`` under the fitted
+        surrogate, by MAP (random unconstrained start; ``restarts=R`` runs R starts as one device batch) or by MCMC
+        over x.  Returns ``(data, xopt)`` or, with ``evaluate_opt``, ``(data, xopt, ysamp)`` after appending the
+        evaluated point to the data set."""
+        if self.verbose:
+            print('Running Bayesian inverse solver...')
+        post = self.inverse_posterior(yobs, yvarobs, jitter)
+        data, mp = self.__x_model_opt(post, method, np.random.default_rng(seed), **kwargs)
+        xopt = np.array([[float(mp[f'x{j}']) for j in range(self.nx)]])
+        verb, self.verbose = self.verbose, False
+        try:
+            ypred = self.predict(xopt)
+        finally:
+            self.verbose = verb
+        if self.verbose:
+            print(f'Predicted {ypred} at x point {xopt}')
+        if evaluate_opt:
+            xsamp, ysamp = self._core__vector_solver(xopt)
+            ym = self.__mean_values(xsamp)
+            self.x = np.r_[self.x, xsamp]
+            self.y = np.r_[self.y, ysamp]
+            self.ym = np.r_[self.ym, ym]
+            self.nsamp = len(self.x)
+            self.__con(len(xsamp))
+            self._pred_cache = None
+            if self.verbose:
+                print(f'Actual evaluation is {ysamp} at x point {xsamp}')
+            return data, xopt[0, :], ysamp[0]
+        return data, xopt[0, :]

@@ -29,7 +29,7 @@ class _Block:
         self.theta_index = np.asarray(theta_index, dtype=np.int64)   # where its entries live in the flat theta
         if family in ('lognormal', 'halfnormal'):
             self.transform, self.tname = 'log', name + '_log__'
-        elif family == 'truncnormal':
+        elif family in ('truncnormal', 'uniform'):
             self.transform, self.tname = 'interval', name + '_interval__'
         else:
             self.transform, self.tname = None, name
@@ -81,6 +81,8 @@ class _Block:
             mu, sg, lo, hi = a
             norm = np.log(_norm_cdf((hi - mu) / sg) - _norm_cdf((lo - mu) / sg))
             return -0.5 * ((x - mu) / sg) ** 2 - np.log(sg) - SQRT2PI_LOG - norm, -(x - mu) / (sg * sg)
+        if f == 'uniform':      # args (unused, unused, lower, upper): same slots as truncnormal for the transform
+            return np.full_like(x, -np.log(a[3] - a[2])), np.zeros_like(x)
         raise ValueError(f)
 
     def moment(self):
@@ -101,6 +103,8 @@ class _Block:
             return np.abs(a[0] * rng.standard_normal(shape))
         if f == 'normal':
             return a[0] + a[1] * rng.standard_normal(shape)
+        if f == 'uniform':
+            return a[2] + (a[3] - a[2]) * rng.uniform(size=shape)
         from scipy.stats import truncnorm
         lo, hi = (a[2] - a[0]) / a[1], (a[3] - a[0]) / a[1]
         return truncnorm(lo, hi, loc=a[0], scale=a[1]).rvs(size=shape, random_state=rng)
@@ -109,6 +113,7 @@ class _Block:
 class ParamSpace:
     """All hyperparameters of one model.  ``pos``: positivity flags of the output-warp parameters in wgp order
     (``wgp.pos``), or None when the output warp is not learnable."""
+    VECTOR_NAMES = ('l', 'kv', 'iwgp', 'cwgp_pos', 'cwgp')   # reported as arrays even when they hold one entry
 
     def __init__(self, nx, nkern, noise, n_iw=0, cw_pos=None, has_alpha=False, truncate=False):
         self.nx, self.nkern, self.noise, self.truncate = nx, nkern, noise, truncate
@@ -144,6 +149,9 @@ class ParamSpace:
         if has_alpha:
             blocks.append(_Block('alpha', 1, 'lognormal', (0.56, 0.75), [p]))
             p += 1
+        self._set_blocks(blocks, p)
+
+    def _set_blocks(self, blocks, p):
         self.blocks = blocks
         self.P = p
         # unconstrained vector: blocks concatenated in creation order
@@ -221,11 +229,11 @@ class ParamSpace:
         out = {}
         for b, sl in zip(self.blocks, self.zslices):
             if b.transform is not None:
-                out[b.tname] = z[sl].copy() if b.size > 1 or b.name in ('l', 'kv', 'iwgp', 'cwgp_pos', 'cwgp') \
+                out[b.tname] = z[sl].copy() if b.size > 1 or b.name in self.VECTOR_NAMES \
                     else np.array(z[sl][0])
         for b, sl in zip(self.blocks, self.zslices):
             x = b.backward(z[sl])[0]
-            out[b.name] = x.copy() if b.size > 1 or b.name in ('l', 'kv', 'iwgp', 'cwgp_pos', 'cwgp') else np.array(x[0])
+            out[b.name] = x.copy() if b.size > 1 or b.name in self.VECTOR_NAMES else np.array(x[0])
         return out
 
     def theta_from_hypers(self, hyp):
@@ -233,3 +241,31 @@ class ParamSpace:
         for b in self.blocks:
             th[b.theta_index] = np.asarray(hyp[b.name], dtype=np.float64).reshape(-1)
         return th
+
+
+class XSpace(ParamSpace):
+    """The unknown input point of the inverse problem / the query point of the BO ``opt_method='map'`` graph as
+    PyMC variables ``x0 .. x{nx-1}``: the scipy priors of the sampler converted as the reference does
+    (andvaranaut/gpmcmc.py:1053-1096 and :706-731): uniform -> pm.Uniform (interval transform), norm -> pm.Normal,
+    truncnorm -> pm.TruncatedNormal (interval transform)."""
+    VECTOR_NAMES = ()
+
+    def __init__(self, priors):
+        blocks = []
+        for k, pr in enumerate(priors):
+            kind = type(pr.dist).__name__
+            if kind == 'uniform_gen':
+                lo, hi = pr.support()
+                blocks.append(_Block(f'x{k}', 1, 'uniform', (0.0, 1.0, float(lo), float(hi)), [k]))
+            elif kind == 'norm_gen':
+                blocks.append(_Block(f'x{k}', 1, 'normal', (float(pr.mean()), float(pr.std())), [k]))
+            elif kind == 'truncnorm_gen':
+                lo, hi = pr.support()
+                # the reference recovers mu / sigma from the frozen distribution's args / kwds case by case
+                # (gpmcmc.py:1063-1091); scipy's own argument parser gives the same (loc, scale)
+                _, loc, scale = pr.dist._parse_args(*pr.args, **pr.kwds)
+                blocks.append(_Block(f'x{k}', 1, 'truncnormal', (float(loc), float(scale), float(lo), float(hi)), [k]))
+            else:
+                raise Exception('Prior distribution conversion from scipy to pymc not implemented')
+        self.nx = len(priors)
+        self._set_blocks(blocks, len(priors))

@@ -394,6 +394,42 @@ def predict_grad(spec: ModelSpec, theta, Xc, z, Xs, pred_noise=True):
     return mu, var, dmu, dvar
 
 
+def inverse_loglik(spec: ModelSpec, theta, Xc, yc, xo_c, yo_c, ynoise, log_yder_sum=0.0):
+    """Potential of the Bayesian inverse problem, literally as the reference builds it (gpmcmc.py:1098-1165):
+    the unknown converted point ``xo_c`` [nx] is appended ``nobs = len(yo_c)`` times to the converted training inputs
+    (:1099-1104, the scalar x prior broadcast into every observation row), the kernel is evaluated on the stacked inputs
+    with the FITTED hyperparameters (:1106-1130), ``ynoise`` [N+nobs] is added to the DIAGONAL as is -- the reference
+    stores square roots of variances in it, quirk 8 of SURVEY app. C (:1137-1158) -- and
+    ``-1/2 y^T K^-1 y - sum log diag L - n/2 log 2 pi + sum log yder`` follows (:1156-1165).  ``spec.jitter`` is not
+    used here: the jitter sits inside ``ynoise``."""
+    th = unpack(spec, theta)
+    nobs = len(yo_c)
+    xin = np.vstack([Xc, np.tile(np.asarray(xo_c, dtype=np.float64)[None, :], (nobs, 1))])
+    yin = np.r_[yc, yo_c]
+    K = cov_matrix(spec, th, xin)
+    K = K + np.diag(ynoise)
+    L = sla.cholesky(K, lower=True, check_finite=False)
+    beta = sla.solve_triangular(L, yin, lower=True, check_finite=False)
+    alpha = sla.solve_triangular(L.T, beta, lower=False, check_finite=False)
+    return (-0.5 * np.dot(yin.T, alpha) - np.sum(np.log(np.diag(L))) - 0.5 * len(yin) * np.log(2 * np.pi)
+            + log_yder_sum)
+
+
+def gh_stats_inv(y, yv, con, deg=8):
+    """``__gh_stats_inv`` (gpmcmc.py:573-585): Gauss-Hermite variance of the CONVERTED observation; the loop
+    overwrites ``yvcon`` so the value of the LAST observation is what comes back (a scalar)."""
+    xi, wi = np.polynomial.hermite.hermgauss(deg)
+    yvcon = None
+    for i in range(len(y)):
+        yi = np.sqrt(2 * yv[i, 0]) * xi + y[i, 0]
+        yir = con(yi)
+        ym = 1 / np.sqrt(np.pi) * np.sum(wi * yir)
+        yir2 = np.power(yir, 2)
+        ym2 = 1 / np.sqrt(np.pi) * np.sum(wi * yir2)
+        yvcon = ym2 - ym ** 2
+    return yvcon
+
+
 def gh_stats_grad(mu, var, dmu, dvar, rev, der, mean_add=None, dmean_add=None, normvar=True, deg=8, EI=False,
                   EIopt=None, yopt=None):
     """:func:`gh_stats` together with the gradient of both outputs w.r.t. the query points, given the gradients of

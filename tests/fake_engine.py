@@ -37,3 +37,7 @@ class OracleEngine:
     def predict(self, Xs, epilogue=None, mean_add=None, **kw):
         mu, var = go.predict(self.spec, self.theta, self.X, self.y, np.asarray(Xs, dtype=np.float64))
         return torch.tensor(mu), torch.tensor(var)
+
+    def predict_grad(self, Xs, epilogue=None, mean_add=None, dmean_add=None, pred_noise=True, **kw):
+        out = go.predict_grad(self.spec, self.theta, self.X, self.y, np.asarray(Xs, dtype=np.float64), pred_noise=pred_noise)
+        return tuple(torch.tensor(a) for a in out)

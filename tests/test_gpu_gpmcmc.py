@@ -197,3 +197,79 @@ def test_acquisition_grad_matches_oracle_graph(tmp_path, method, opt_type):
         h[i] = hh
         fd = (oracle_value(x + h) - oracle_value(x - h)) / (2 * hh)
         assert np.max(np.abs(gr[:, i] - fd)) <= tol * max(np.max(np.abs(fd)), np.max(np.abs(gr))), (i, gr[:, i], fd)
+
+
+def test_nuts_fit_on_device(tmp_path):
+    """fit(method='mcmc_mean') with the lock-step NUTS driver (default sampler): every leapfrog of every chain is one
+    batched device call; trajectory lengths differ between chains, draws are finite and predictive."""
+    g = tutorial_gp(tmp_path, kernel='Matern52', noise=True, n=40)
+    data = g.fit(method='mcmc_mean', draws=40, tune=80, chains=8, seed=3, sampler='nuts', max_treedepth=6,
+                 return_data=True)
+    n = data.sample_stats['n_steps']
+    assert n.shape == (8, 40) and n.min() >= 1 and n.max() <= 63 and len(np.unique(n)) > 1
+    assert np.isfinite(data.sample_stats['lp']).all() and data.sample_stats['acceptance_rate'].mean() > 0.5
+    y = g.predict(g.x[:5])
+    assert np.max(np.abs(y[:, 0] - g.y[:5, 0])) < 2e-2
+
+
+@pytest.mark.parametrize('with_var', [False, True])
+def test_inverse_posterior_matches_oracle_graph(tmp_path, with_var):
+    """inverse_opt's model (gpmcmc.py:1049-1165) on the device (one factorisation + batched predict_grad, block form)
+    against the oracle's literal dense restatement: logp over the unconstrained x to 1e-9, gradient to central
+    differences of the oracle."""
+    g = tutorial_gp(tmp_path, kernel='Matern52', noise=True, n=60)
+    g.fit()
+    yobs = np.array([[0.35]])
+    yvar = np.array([[1e-3]]) if with_var else None
+    post = g.inverse_posterior(yobs, yvar)
+    spec = go.ModelSpec(nx=2, kerns=['Matern52'], noise=True, jitter=0.0)
+    sp = ParamSpace(2, 1, True)
+    th = sp.theta_from_hypers(g.hypers)
+    c = g.yconrevs[0]
+    noise_o = np.sqrt(go.gh_stats_inv(yobs, yvar, c.con)) if with_var else 0.0
+    ynoise = np.r_[np.full(60, np.sqrt(g.hypers['gv'] + 1e-6)), noise_o]
+    lyd = np.sum(np.log(c.der(np.r_[g.y[:, 0], yobs[:, 0]])))
+
+    def oracle_logp(z):
+        x = post.space.theta_from_z(z)[0]
+        xc = np.array([g.xconrevs[i].con(x[i:i + 1])[0] for i in range(2)])
+        return go.inverse_loglik(spec, th, g.xc, g.yc[:, 0], xc, c.con(yobs[:, 0]), ynoise, lyd) \
+            + post.space.prior(x)[0]
+
+    rng = np.random.default_rng(6)
+    z = rng.normal(size=(9, 2))
+    v, gr, _ = post.logp_dlogp(z, False)
+    ref = np.array([oracle_logp(zz) for zz in z])
+    assert np.max(np.abs(v - ref)) <= 1e-9 * np.max(np.abs(ref)), (v, ref)
+    # e^2 / s with a small predictive variance s: the dense oracle's central differences carry ~1e-10 / h of rounding
+    # noise relative to gradients of O(1e3), so the step is 1e-4 (truncation ~1e-7, measured on the CPU twin of this test)
+    for i in range(2):
+        h = np.zeros(2)
+        h[i] = 1e-4
+        fd = np.array([(oracle_logp(zz + h) - oracle_logp(zz - h)) / 2e-4 for zz in z])
+        assert np.max(np.abs(gr[:, i] - fd)) <= 5e-5 * max(1.0, np.max(np.abs(fd))), (gr[:, i], fd)
+
+
+def test_inverse_opt_recovers_an_input_that_explains_the_observation(tmp_path):
+    g = tutorial_gp(tmp_path, kernel='RBF', noise=True, n=80)
+    g.fit()
+    xtrue = np.array([1.3, 1.2])
+    yobs = np.array([target_fun(xtrue)])
+    data, xopt = g.inverse_opt(yobs, method='map', restarts=6, seed=1)
+    assert xopt.shape == (2,) and set(data) == {'x0', 'x1', 'x0_interval__', 'x1_interval__'}
+    assert abs(g.predict(xopt[None, :])[0, 0] - yobs[0, 0]) < 5e-3
+    n0 = len(g.x)
+    data, xopt, ysamp = g.inverse_opt(yobs, yvarobs=np.array([[1e-4]]), method='mcmc_mean', evaluate_opt=True,
+                                      draws=40, tune=60, chains=4, seed=2)
+    assert data.posterior['x0'].shape == (4, 40) and len(g.x) == n0 + 1 and len(g.xc) == n0 + 1
+    assert np.allclose(g.x[-1], xopt) and np.isfinite(ysamp).all()
+
+
+def test_bo_with_the_acquisition_model(tmp_path):
+    """BO(opt_method='map'): candidates from find_MAP over the x model with the device acquisition as Potential
+    (gpmcmc.py:699-858), instead of LHC candidates."""
+    g = tutorial_gp(tmp_path, kernel='Matern52', noise=True, n=30)
+    g.fit()
+    y0 = float(np.min(g.y))
+    xopt, yopt = g.BO(opt_type='min', opt_method='map', max_iter=3, method='EI', seed=4, restarts=4)
+    assert len(g.x) > 30 and yopt <= y0

@@ -182,3 +182,138 @@ def test_sharding_world_size_2_gloo_equals_single_process():
         assert np.array_equal(r[1], ll.numpy()) and np.array_equal(r[2], g.numpy()) and np.array_equal(r[3], info.numpy())
         assert np.array_equal(r[4], mu.numpy()) and np.array_equal(r[5], var.numpy())
     assert res[0][6][0] == 3 and res[1][6][0] == 2      # 5 samples split 3 + 2
+
+
+# ---- x models: inverse problem, BO 'map' acquisition model, NUTS ------------------------------------------------
+def test_xspace_follows_the_reference_prior_conversion():
+    """gpmcmc.py:1053-1096: uniform -> Uniform(support), norm -> Normal(mean, std), truncnorm -> TruncatedNormal with
+    (mu, sigma) recovered from args / kwds in every calling convention the reference distinguishes."""
+    from andvaranaut_b200.priors import XSpace
+    tn = [st.truncnorm(-1.0, 2.0, 0.5, 0.2), st.truncnorm(-1.0, 2.0, 0.5, scale=0.2), st.truncnorm(-1.0, 2.0, 0.5),
+          st.truncnorm(a=-1.0, b=2.0, loc=0.5, scale=0.2), st.truncnorm(-1.0, 2.0), st.truncnorm(-1.0, b=2.0, scale=0.2)]
+    expect = [(0.5, 0.2), (0.5, 0.2), (0.5, 1.0), (0.5, 0.2), (0.0, 1.0), (0.0, 0.2)]
+    sp = XSpace([st.uniform(1.0, 0.5), st.norm(2.0, 3.0)] + tn)
+    assert [b.name for b in sp.blocks] == [f'x{k}' for k in range(8)]
+    assert sp.blocks[0].family == 'uniform' and sp.blocks[0].args[2:] == (1.0, 1.5)
+    assert sp.blocks[1].family == 'normal' and sp.blocks[1].args == (2.0, 3.0)
+    for b, pr, (mu, sg) in zip(sp.blocks[2:], tn, expect):
+        assert b.family == 'truncnormal' and np.allclose(b.args, (mu, sg, mu - sg, mu + 2 * sg))
+    # densities against scipy, names as PyMC reports them
+    rng = np.random.default_rng(1)
+    z = rng.normal(size=sp.P)
+    x, dxdz, ljac, dljac = sp.theta_from_z(z)
+    lp, _ = sp.prior(x)
+    ref = st.uniform(1.0, 0.5).logpdf(x[0]) + st.norm(2.0, 3.0).logpdf(x[1]) + sum(p.logpdf(v) for p, v in zip(tn, x[2:]))
+    assert np.isclose(lp, ref, rtol=1e-12)
+    h = sp.hypers_dict(z)
+    assert set(h) == {f'x{k}' for k in range(8)} | {'x0_interval__'} | {f'x{k}_interval__' for k in range(2, 8)}
+    assert h['x0'].shape == ()
+    with pytest.raises(Exception, match='not implemented'):
+        XSpace([st.beta(2, 3)])
+
+
+def _inverse_case(kerns, ops, nobs, with_var):
+    rng = np.random.default_rng(8)
+    N, d = 40, 2
+    X = rng.uniform(0.05, 0.95, size=(N, d))
+    y = np.sin(3 * X[:, 0]) + X[:, 1] ** 2 + 0.01 * rng.normal(size=N)
+    nk = len(kerns)
+    hyp = dict(gv=np.array(2e-4), l=rng.uniform(0.4, 0.9, d * nk), kv=rng.uniform(0.8, 1.5, nk))
+    if 'RatQuad' in kerns:
+        hyp['alpha'] = np.array(1.7)
+    yo = np.full(nobs, 0.9) + 0.01 * np.arange(nobs)
+    noise_o = 3e-3 if with_var else 0.0
+    return X, y, hyp, yo, noise_o
+
+
+@pytest.mark.parametrize('kerns,ops,nobs,with_var', [(['RBF'], [], 1, False), (['Matern52'], [], 1, True),
+                                                    (['Matern32', 'RBF'], ['+'], 3, True),
+                                                    (['Exponential', 'RatQuad'], ['*'], 2, True)])
+def test_inverse_likelihood_block_form_equals_dense_reference_graph(kerns, ops, nobs, with_var):
+    """The block (Schur) evaluation of the inverse-problem potential == the oracle's literal restatement of
+    gpmcmc.py:1098-1165 (dense Cholesky of the stacked system), incl. the sqrt-variance-on-the-diagonal quirk and the
+    full-form kernel diagonal; gradient against central differences.  Engine = oracle test double (CPU)."""
+    from andvaranaut_b200.xpost import InverseLikelihood, kdiag_values
+    X, y, hyp, yo, noise_o = _inverse_case(kerns, ops, nobs, with_var)
+    jitter = 1e-6
+    d = X.shape[1]
+    noise_t = np.sqrt(hyp['gv'] + jitter)
+    spec = go.ModelSpec(nx=d, kerns=kerns, ops=ops, noise=True, jitter=0.0)
+    sp = ParamSpace(d, len(kerns), True, has_alpha='RatQuad' in kerns)
+    th = sp.theta_from_hypers(dict(hyp, gv=noise_t))
+    eng = OracleEngine(spec)
+    eng.set_data(X, y)
+    eng.factorize(th)
+    const = go.loglik(spec, th, X, y, want_grad=False).ll
+    cfull, cdiag = kdiag_values(kerns, ops, hyp['kv'], float(hyp.get('alpha', 1.0)))
+    # a conversion with a non-trivial derivative: xc = x^2 on [0,1]
+    pot = InverseLikelihood(eng, lambda x: (x ** 2, 2 * x), yo, noise_o, cfull - cdiag, const)
+    xq = np.random.default_rng(2).uniform(0.2, 0.9, size=(5, d))
+    val, gx = pot(xq)
+    ynoise = np.r_[np.full(len(y), noise_t), np.full(nobs, noise_o)]
+    th_ref = sp.theta_from_hypers(hyp)
+
+    def dense(x):
+        return go.inverse_loglik(spec, th_ref, X, y, x ** 2, yo, ynoise)
+    ref = np.array([dense(x) for x in xq])
+    assert np.max(np.abs(val - ref)) <= 1e-9 * np.max(np.abs(ref))
+    for i in range(d):
+        h = np.zeros(d)
+        h[i] = 1e-6
+        fd = np.array([(dense(x + h) - dense(x - h)) / 2e-6 for x in xq])
+        # the Exponential kernel's cusp at training points makes the central difference itself only ~1e-5 accurate
+        tol = 1e-4 if 'Exponential' in kerns else 1e-5
+        assert np.max(np.abs(gx[:, i] - fd)) <= tol * max(1.0, np.max(np.abs(fd)))
+
+
+def test_inverse_map_and_nuts_recover_the_point():
+    """find_map / NUTS over the x model: a 1-observation inverse problem on a monotone response has its posterior
+    mass where the surrogate reproduces the observation."""
+    from andvaranaut_b200.xpost import InverseLikelihood, XPosterior, kdiag_values
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 1, size=(30, 1))
+    y = 2.0 * X[:, 0] + 0.3 * X[:, 0] ** 2
+    hyp = dict(gv=np.array(1e-5), l=np.array([1.2]), kv=np.array([3.0]))
+    spec = go.ModelSpec(nx=1, kerns=['RBF'], noise=True, jitter=0.0)
+    sp = ParamSpace(1, 1, True)
+    th = sp.theta_from_hypers(dict(hyp, gv=np.sqrt(hyp['gv'] + 1e-6)))
+    eng = OracleEngine(spec)
+    eng.set_data(X, y)
+    eng.factorize(th)
+    xtrue = 0.62
+    yo = np.array([2.0 * xtrue + 0.3 * xtrue ** 2])
+    pot = InverseLikelihood(eng, lambda x: (x, np.ones_like(x)), yo, 0.0, 0.0, 0.0)
+    post = XPosterior([st.uniform(0, 1)], pot)
+    zs, lps = drivers.find_map_multi(post, rng.standard_normal((4, 1)))
+    xs = post.space.theta_from_z(zs)[0][:, 0]
+    assert np.all(np.abs(xs - xtrue) < 0.02), xs
+    tr = drivers.sample(post, draws=120, tune=150, chains=6, seed=4)
+    xm = tr.posterior['x0']
+    assert xm.shape == (6, 120) and abs(xm.mean() - xtrue) < 0.03
+    assert 'x0_interval__' in tr.posterior and tr.sample_stats['diverging'].mean() < 0.05
+
+
+def test_nuts_and_hmc_sample_a_known_density():
+    """lock-step NUTS (default) and HMC on a correlated Gaussian x a uniform: means, variances, covariance."""
+    from andvaranaut_b200.xpost import XPosterior
+
+    def pot(x):
+        dlt = x[:, 0] - x[:, 1]
+        g = np.zeros_like(x)
+        g[:, 0], g[:, 1] = -dlt, dlt
+        return -0.5 * dlt * dlt, g
+    lam = np.array([[1.25, -1.0], [-1.0, 5.0]])
+    cov = np.linalg.inv(lam)
+    mean = cov @ np.array([0.25, -4.0])
+    for smp in ('nuts', 'hmc'):
+        post = XPosterior([st.norm(1, 2), st.norm(-1, 0.5), st.uniform(0, 1)], pot)
+        tr = drivers.sample(post, draws=400, tune=300, chains=16, seed=3, sampler=smp, max_leapfrog=16)
+        x = np.stack([tr.posterior[f'x{k}'] for k in range(3)], -1).reshape(-1, 3)
+        assert np.allclose(x.mean(0), np.r_[mean, 0.5], atol=0.06), (smp, x.mean(0))
+        assert np.allclose(x.var(0), np.r_[np.diag(cov), 1 / 12], rtol=0.15), (smp, x.var(0))
+        assert abs(np.cov(x[:, 0], x[:, 1])[0, 1] - cov[0, 1]) < 0.04
+        assert 0.6 < tr.sample_stats['acceptance_rate'].mean() < 0.95
+        if smp == 'nuts':
+            n = tr.sample_stats['n_steps']
+            assert n.min() >= 1 and n.max() <= 1023 and np.all(tr.sample_stats['tree_depth'] <= 10)
+            assert len(np.unique(n)) > 1            # chains stop at different depths within one lock-step transition
