@@ -949,6 +949,61 @@ __global__ void __launch_bounds__(256) predict_grad_kernel(KernDesc kd, int N, i
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Rank-1 extension of a factorised state by ONE training point, hyperparameters unchanged (the data
+// appends of BO / inverse_opt, gpmcmc.py:881-904 / :1197-1205, between two fits):
+//     L' = [[L, 0], [v^T, lam]],  v = T k,  lam^2 = (c + gv + jitter) - |v|^2
+//     T' = [[T, 0], [-(T^T v)^T / lam, 1 / lam]],  alpha' = [alpha - w bn / lam ; bn / lam],  bn = (z_new - k^T alpha) / lam
+// k, mu = k^T alpha, v, |v|^2 and w = T^T v come from the predict kernels run on the new point as a one-column panel
+// (kxs_kernel, predict_v_kernel, ttv_kernel); this kernel writes row N of T, the alpha update and the scaled
+// inputs of the new row.  Needs N < npad (room in the padded slab).  grid (npad / 256), one column per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) append_kernel(KernDesc kd, int N, int npad, const HypS* __restrict__ hyp_g,
+                                                     const double* __restrict__ xnew, const double* __restrict__ znew,
+                                                     const double* __restrict__ Wm, int mld,
+                                                     const double* __restrict__ mu_var, double* __restrict__ T,
+                                                     double* __restrict__ alpha, double* __restrict__ xs,
+                                                     double* __restrict__ x2, int32_t* __restrict__ info) {
+  __shared__ HypS hyp;
+  __shared__ double sx[MAXK][MAXD | 1];
+  __shared__ double sx2[MAXK];
+  const int tid = threadIdx.x, j = blockIdx.x * 256 + tid;
+  for (int e = tid; e < (int)(sizeof(HypS) / sizeof(double)); e += 256)
+    reinterpret_cast<double*>(&hyp)[e] = reinterpret_cast<const double*>(hyp_g)[e];
+  __syncthreads();
+  if (tid < kd.nkern) {
+    double tmp[MAXD];
+    for (int m = 0; m < kd.d; m++) {
+      tmp[m] = __dmul_rn(xnew[m], hyp.invl[tid][m]);
+      sx[tid][m] = tmp[m];
+    }
+    sx2[tid] = sumsq_numpy_order(tmp, kd.d);
+  }
+  __syncthreads();
+  // diagonal entry exactly as cov_kernel builds it: full-form kernel value at r2 = 0, then + (gv + jitter)
+  const double c = cov_fold(kd, hyp, &sx[0][0], MAXD | 1, sx2, 1, &sx[0][0], MAXD | 1, sx2, 1);
+  const double vv = kdiag_total(kd, hyp) - mu_var[1];          // |v|^2 (predict_v_kernel stores kdiag - |v|^2)
+  const double s = __dadd_rn(c, hyp.gv + kd.jitter) - vv;
+  if (!(s > 0.0)) {
+    if (j == 0) info[0] = N + 1;
+    return;
+  }
+  const double lam = sqrt(s), bn = (znew[0] - mu_var[0]) / lam;
+  if (j < N) {
+    const double w = Wm[(int64_t)j * mld];
+    T[(int64_t)N * npad + j] = -w / lam;
+    alpha[j] -= w * bn / lam;
+  } else if (j == N) {
+    T[(int64_t)N * npad + N] = 1.0 / lam;
+    alpha[N] = bn / lam;
+    for (int k = 0; k < kd.nkern; k++) {
+      for (int m = 0; m < kd.d; m++) xs[((int64_t)k * npad + N) * kd.d + m] = sx[k][m];
+      x2[(int64_t)k * npad + N] = sx2[k];
+    }
+  }
+}
+
 }  // namespace avn
 
 #include "kinv_fast.cuh"

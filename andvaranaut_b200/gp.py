@@ -124,7 +124,7 @@ class GPEngine:
             return a.to(device=self.device, dtype=torch.float64).contiguous()
         return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
 
-    def set_data(self, X, y):
+    def set_data(self, X, y, _keep_state=False):
         X = self._dev(X)
         y = self._dev(y).reshape(-1)
         if X.ndim != 2 or X.shape[1] != self.nx or X.shape[0] != y.shape[0]:
@@ -133,7 +133,8 @@ class GPEngine:
         rc = self.lib.avn_gp_set_data(self._h, _ptr(X), _ptr(y), self.N)
         if rc != 0:
             raise GPError(_lib.last_error())
-        self._state = None
+        if not _keep_state:
+            self._state = None
 
     @property
     def npad(self):
@@ -229,6 +230,42 @@ class GPEngine:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         self._theta_fact = theta
+        return info
+
+    def append(self, xnew, znew):
+        """Extend the factorised state by one converted training point (hyperparameters unchanged): O(N^2) rank-1
+        update of T = L^-1 and alpha in place (``avn_gp_append``); a full refactorisation only when the padded slab
+        is full (every 64th point) .  Returns info (device int32 [1]): non-zero = new pivot not positive, in which
+        case the engine is left on the OLD data set."""
+        if self._state is None:
+            raise GPError('factorize first')
+        xnew = self._dev(xnew).reshape(-1)
+        znew = self._dev(np.asarray(znew, dtype=np.float64).reshape(-1)[:1]) if not isinstance(znew, torch.Tensor) \
+            else self._dev(znew).reshape(-1)[:1]
+        if xnew.shape[0] != self.nx:
+            raise ValueError('xnew must have nx entries')
+        Xn = torch.cat([self._X, xnew[None, :]])
+        yn = torch.cat([self._y, znew])
+        need = self.lib.avn_gp_append_workspace_bytes(self._h)
+        if self._pws is None or self._pws.numel() < need:
+            self._pws = None
+            self._pws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        rc = self.lib.avn_gp_append(self._h, _ptr(self._state), self._state.numel(), _ptr(xnew), _ptr(znew), _ptr(info),
+                                    _ptr(self._pws), self._pws.numel(), _stream())
+        if rc < 0:
+            raise GPError(_lib.last_error())
+        if rc == 1:                       # slab full: npad grows, new layout
+            Xo, yo = self._X, self._y
+            self.set_data(Xn, yn)
+            info = self.factorize(self._theta_fact)
+            if int(info[0]) != 0:
+                self.set_data(Xo, yo)
+                self.factorize(self._theta_fact)
+            return info
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        if int(info[0]) == 0:
+            self.set_data(Xn, yn, _keep_state=True)
         return info
 
     @staticmethod

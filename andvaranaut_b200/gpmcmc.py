@@ -219,7 +219,8 @@ class GPMCMC(LHC):
             restarts=1, **kwargs):
         self.m, self.gp, self.hypers, data = self.__fit(self.x, self.y - self.ym, method, iwgp, cwgp, jitter,
                                                         truncate, restarts, **kwargs)
-        self._pred_cache = None
+        if method != 'none':       # unchanged hypers and conrevs: the factorised state stays valid (and is EXTENDED by
+            self._pred_cache = None  # rank-1 appends when points were added since, see _predict_engine)
         if return_data:
             return data
 
@@ -351,6 +352,20 @@ class GPMCMC(LHC):
         key = (jitter, len(self.xc))
         if self._pred_cache is not None and self._pred_cache[0] == key:
             return self._pred_cache[1], self._pred_cache[2]
+        if self._pred_cache is not None and self._pred_cache[0][0] == jitter \
+                and 0 < len(self.xc) - self._pred_cache[0][1] <= 64:
+            # points were appended (BO / inverse_opt / fit_method='none') under unchanged hypers and conversions:
+            # rank-1 extension of the cached factorisation, O(N^2) per point
+            (_, n0), eng, th = self._pred_cache
+            ok = True
+            for i in range(n0, len(self.xc)):
+                if int(eng.append(self.xc[i], self.yc[i, 0])[0]) != 0:
+                    ok = False
+                    break
+            if ok:
+                self._pred_cache = (key, eng, th)
+                return eng, th
+            self._pred_cache = None
         from .gp import GPEngine
         eng = GPEngine(nx=self.nx, kerns=self.kerns, ops=self.ops, noise=self.noise, jitter=jitter, device=self.device)
         eng.set_data(self.xc, self.yc[:, 0])
@@ -757,7 +772,6 @@ class GPMCMC(LHC):
             self.ym = np.r_[self.ym, ym]
             self.nsamp = len(self.x)
             self.__con(len(xsamp))
-            self._pred_cache = None
             if self.verbose:
                 print(f'Actual evaluation is {ysamp} at x point {xsamp}')
             return data, xopt[0, :], ysamp[0]

@@ -145,6 +145,18 @@ int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const double* Xs_dev,
                         double* out_mean_dev, double* out_var_dev, double* out_dmean_dev, double* out_dvar_dev,
                         void* ws_dev, size_t ws_bytes, void* stream);
 
+/* Rank-1 extension of a factorised state by ONE training point with the hyperparameters unchanged: what the data
+ * appends of BO / inverse_opt (gpmcmc.py:881-904, :1197-1205) need between two fits when fit_method = 'none' --
+ * O(N^2) instead of the O(N^3) refactorisation the reference performs inside every predict call (:588-598).
+ * xnew [d] converted inputs, znew [1] converted output (both DEVICE memory).  Works in place on state_dev.
+ * Returns 1 (nothing done) when the padded slab is full, N % AVN_TILE == 0: the caller then refactorises with
+ * N + 1 points.  info[0] = N + 1 if the new pivot is not positive (state unchanged).  The handle is NOT modified:
+ * after a successful append the caller registers the N + 1-row arrays with avn_gp_set_data (stream-ordered, the
+ * state buffer keeps its size because npad is unchanged). */
+size_t avn_gp_append_workspace_bytes(const avn_gp* gp);
+int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, const double* xnew_dev, const double* znew_dev,
+                  int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* introspection used by bench.py: number of kernel launches issued by the last call on this handle */
 int64_t avn_gp_last_launch_count(const avn_gp* gp);
 

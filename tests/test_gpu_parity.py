@@ -364,3 +364,63 @@ def test_predict_grad_epilogues():
                 assert np.max(np.abs(v - rv)) <= 1e-8 * max(np.max(np.abs(rv)), np.max(rm ** 2)), (stages, kw)
                 assert np.max(np.abs(dm - rdm)) <= 1e-8 * np.max(np.abs(rdm)), (stages, kw)
                 assert np.max(np.abs(dv - rdv)) <= 1e-7 * max(np.max(np.abs(rdv)), np.max(np.abs(rdm))), (stages, kw)
+
+
+@pytest.mark.parametrize('name,N0,nadd', [('rbf', 100, 40), ('m52', 60, 70), ('sum', 120, 9)])
+def test_rank1_append_equals_refactorisation(name, N0, nadd):
+    """avn_gp_append: extending the factorised state point by point == factorising the enlarged data set
+    (the reference refactorises inside every predict, gpmcmc.py:588-598), checked on the predictions against the
+    oracle on ALL points; the runs cross a 64-row slab boundary (N0 + nadd > next multiple of 64), where the engine
+    falls back to one refactorisation."""
+    from andvaranaut_b200.gp import GPEngine
+    kerns, ops = {'rbf': (['RBF'], []), 'm52': (['Matern52'], []), 'sum': (['Matern32', 'RBF'], ['+'])}[name]
+    d = 3
+    rng = np.random.default_rng(N0)
+    X = rng.uniform(size=(N0 + nadd, d))
+    y = np.sin(X @ np.array([2.0, 1.0, 3.0])) + 0.01 * rng.normal(size=N0 + nadd)
+    spec = go.ModelSpec(nx=d, kerns=kerns, ops=ops, noise=True)
+    nk = len(kerns)
+    th = np.r_[1e-3, rng.uniform(0.4, 1.0, d * nk), rng.uniform(0.8, 1.5, nk)]
+    eng = GPEngine(nx=d, kerns=kerns, ops=ops, noise=True)
+    eng.set_data(X[:N0], y[:N0])
+    assert int(eng.factorize(th)[0]) == 0
+    Xs = rng.uniform(size=(77, d))
+    launches = []
+    for i in range(N0, N0 + nadd):
+        assert int(eng.append(X[i], y[i])[0]) == 0
+        launches.append(eng.launches)
+        if i in (N0, N0 + nadd // 2):                     # intermediate states are valid too
+            mu, var = (t.cpu().numpy() for t in eng.predict(Xs))
+            rmu, rvar = go.predict(spec, th, X[:i + 1], y[:i + 1], Xs)
+            assert np.max(np.abs(mu - rmu)) <= 1e-8 * np.max(np.abs(rmu))
+            assert np.max(np.abs(var - rvar)) <= 1e-8 * np.max(np.maximum(np.abs(rvar), th[1 + d * nk]))
+    assert eng.N == N0 + nadd and min(launches) == 4      # kxs, V = T k, w = T^T v, append
+    mu, var = (t.cpu().numpy() for t in eng.predict(Xs))
+    rmu, rvar = go.predict(spec, th, X, y, Xs)
+    assert np.max(np.abs(mu - rmu)) <= 1e-8 * np.max(np.abs(rmu))
+    assert np.max(np.abs(var - rvar)) <= 1e-8 * np.max(np.maximum(np.abs(rvar), th[1 + d * nk]))
+    # and the likelihood path sees the enlarged data set
+    ll, _, info = eng.loglik_grad(th[None, :], want_grad=False)
+    assert abs(float(ll[0]) - go.loglik(spec, th, X, y, want_grad=False).ll) <= 1e-9 * abs(float(ll[0]))
+
+
+def test_rank1_append_rejects_a_non_positive_pivot():
+    """a duplicate of a training point without noise or jitter: the new pivot is zero up to rounding; when the update
+    reports it (info = N + 1) the state and the data set are left as they were."""
+    from andvaranaut_b200.gp import GPEngine
+    rng = np.random.default_rng(4)
+    X = rng.uniform(size=(50, 2))
+    y = np.sin(3 * X[:, 0]) + X[:, 1]
+    spec = go.ModelSpec(nx=2, kerns=['RBF'], noise=False, jitter=0.0)
+    th = np.array([0.3, 0.35, 1.0])
+    eng = GPEngine(nx=2, kerns=['RBF'], noise=False, jitter=0.0)
+    eng.set_data(X, y)
+    assert int(eng.factorize(th)[0]) == 0
+    Xs = rng.uniform(size=(10, 2))
+    mu0 = eng.predict(Xs)[0].cpu().numpy()
+    info = int(eng.append(X[7], y[7])[0])
+    if info != 0:
+        assert info == 51 and eng.N == 50
+        assert np.array_equal(eng.predict(Xs)[0].cpu().numpy(), mu0)
+    else:
+        assert eng.N == 51
