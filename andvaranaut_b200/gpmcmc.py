@@ -3,18 +3,19 @@ B200-native engine instead of PyMC/PyTensor.
 
 Kept from the reference (same names, arguments, defaults, error messages where they are part of the contract):
 constructor (:31-40), ``set_data`` (:122-137), ``sample`` (:158-172), ``fit`` (:175-182, model semantics of
-``__fit`` :185-401), ``predict`` (:522-542), ``BO`` (:601-906), ``change_model`` (:472-519),
-``change_conrevs/xconrevs/yconrevs`` (:75-95), ``cwgp_set/iwgp_set`` (:433-462), ``train_test`` (:465-469),
-``mean_extract/map_extract`` (:404-430), ``del_samples`` (:57-72), ``relative_importances``, ``test_metrics``
-(the numeric half of ``test_plots`` :933-1028; plotting is out of scope).
+``__fit`` :185-401), ``predict`` (:522-542), ``BO`` (:601-906), ``inverse_opt`` (:1040-1217), ``change_model``
+(:472-519), ``change_conrevs/xconrevs/yconrevs`` (:75-95), ``cwgp_set/iwgp_set`` (:433-462), ``train_test``
+(:465-469), ``mean_extract/map_extract`` (:404-430), ``del_samples`` (:57-72), ``relative_importances``,
+``test_metrics`` (the numeric half of ``test_plots`` :933-1028; plotting is out of scope).
 
 Replaced: the PyMC model (``self.m``) is a :class:`~andvaranaut_b200.priors.ParamSpace` + :class:`GPEngine`
-(``self.gp``); ``pm.find_MAP`` / ``pm.sample`` are :mod:`andvaranaut_b200.drivers`; ``gp.predict`` and the
-per-point Python loop ``__gh_stats`` (:545-569) are one device call.  Documented deviations: ``seed`` is
-honoured by ``sample``; ``restarts > 1`` really restarts from different (prior-drawn) points (the reference
-builds a start and never passes it on, :330-332); the BO ``refine`` step polishes the candidate with bounded
-L-BFGS-B on the reference's own inline acquisition graph (:738-829) evaluated on the device with its analytic
-gradient w.r.t. the query point (:meth:`GPMCMC.acquisition_grad`) instead of a PyMC model over x.
+(``self.gp``); ``pm.find_MAP`` / ``pm.sample`` are :mod:`andvaranaut_b200.drivers` (L-BFGS-B, lock-step NUTS);
+``gp.predict`` and the per-point Python loop ``__gh_stats`` (:545-569) are one device call; the PyMC models over the
+query point x (BO refine / ``opt_method='map'`` :699-858, ``inverse_opt`` :1049-1165) are
+:class:`~andvaranaut_b200.xpost.XPosterior` objects whose potential is evaluated on the device with its analytic
+gradient.  Documented deviations: ``seed`` is honoured by ``sample``; ``restarts > 1`` really restarts from different
+(prior-drawn) points (the reference builds a start and never passes it on, :330-332); the factorisation behind
+``predict`` is cached and extended by rank-1 appends instead of being rebuilt on every call (:588-598).
 """
 import copy
 import re
