@@ -756,7 +756,8 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
 // ---- rank-1 append ------------------------------------------------------------------------
 extern "C" size_t avn_gp_append_workspace_bytes(const avn_gp* gp) {
   if (!gp || gp->N < 1) return 0;
-  return (size_t)(2 * npad_of(gp->N) * TILE * 8 + 256);
+  const int64_t npad = npad_of(gp->N);
+  return (size_t)((3 * npad + 2 * (npad / TILE) + (npad + 255) / 256 + 32) * 8);
 }
 
 extern "C" int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, const double* xnew_dev,
@@ -765,7 +766,7 @@ extern "C" int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, co
   if (gp->N < 1) return fail("avn_gp_append: set_data first");
   if (gp->has_xwarp || gp->kd.n_cw > 0) return fail("avn_gp_append: works on converted data (as avn_gp_factorize)");
   const KernDesc& kd = gp->kd;
-  const int64_t N = gp->N, npad = npad_of(N);
+  const int64_t N = gp->N, npad = npad_of(N), nb = npad / TILE;
   if (N == npad) return 1;  // the padded slab is full: the caller refactorises with N + 1 points
   StateLayout S = state_layout(gp);
   if (state_bytes < (size_t)S.total) return fail("avn_gp_append: state buffer too small");
@@ -779,27 +780,22 @@ extern "C" int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, co
   double* xs = reinterpret_cast<double*>(sb + S.xs);
   double* x2 = reinterpret_cast<double*>(sb + S.x2);
   double* T = reinterpret_cast<double*>(sb + S.t);
-  double* Kxs = static_cast<double*>(ws_dev);  // k, later w = T^T v (column 0 of a 64-column panel)
-  double* V = Kxs + npad * TILE;
-  double* mu_var = V + npad * TILE;            // [0] = k^T alpha, [1] = kdiag - |v|^2
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = opt_in_smem(predict_v_kernel, PredG::SMEM_BYTES);
-    if (e == cudaSuccess) e = opt_in_smem(ttv_kernel, TtvG::SMEM_BYTES);
-    if (e != cudaSuccess) return fail_cuda("append smem opt-in", e);
-    attr_done = true;
-  }
+  double* kvec = static_cast<double*>(ws_dev);
+  double* v = kvec + npad;
+  double* w = v + npad;
+  double* fpart = w + npad;        // [nb][2], slot 0 = block partial of |v|^2
+  double* mu_part = fpart + 2 * nb;  // block partials of k^T alpha
+  const unsigned nblk = (unsigned)((npad + 255) / 256);
   cudaError_t e = cudaMemsetAsync(info_dev, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return fail_cuda("memset info", e);
-  const size_t smem_kxs = (size_t)(kd.nkern * TILE * (kd.d | 1) + kd.nkern * TILE) * 8;
-  kxs_kernel<<<1, 256, smem_kxs, st>>>(kd, (int)N, (int)npad, hyp, xs, x2, alpha, xnew_dev, 1, 0, TILE, Kxs, mu_var);
-  LAUNCH_CHECK("kxs_kernel");
-  predict_v_kernel<<<1, PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(kd, (int)npad, hyp, T, Kxs, TILE, 1, 0, 0, V, mu_var + 1);
-  LAUNCH_CHECK("predict_v_kernel");
-  ttv_kernel<<<dim3(1, (unsigned)(npad / TILE)), TtvG::NTHREADS, TtvG::SMEM_BYTES, st>>>((int)npad, T, V, TILE, Kxs);
-  LAUNCH_CHECK("ttv_kernel");
-  append_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(kd, (int)N, (int)npad, hyp, xnew_dev, znew_dev, Kxs, TILE,
-                                                               mu_var, T, alpha, xs, x2, info_dev);
+  kvec_kernel<<<nblk, 256, 0, st>>>(kd, (int)N, (int)npad, hyp, xs, x2, alpha, xnew_dev, kvec, mu_part);
+  LAUNCH_CHECK("kvec_kernel");
+  beta_kernel<<<dim3((unsigned)nb, 1), 256, 0, st>>>(T, kvec, (int)npad, v, fpart);
+  LAUNCH_CHECK("beta_kernel");
+  alpha_kernel<<<dim3((unsigned)nb, 1), 256, 0, st>>>(T, v, (int)npad, w);
+  LAUNCH_CHECK("alpha_kernel");
+  append_kernel<<<nblk, 256, 0, st>>>(kd, (int)N, (int)npad, hyp, xnew_dev, znew_dev, w, mu_part, fpart, T, alpha, xs, x2,
+                                      info_dev);
   LAUNCH_CHECK("append_kernel");
   return 0;
 }

@@ -455,6 +455,65 @@ def main():
                 'sample': '8192 of the test points in 2 blocks of 4096, L factorised once beforehand '
                           f'({t_fact:.1f} s, not counted), vectorised GH epilogue',
                 'factorize_s': t_fact, 'reference_gh_loop_pts_per_s': 10000 / t_loop}
+        # "next" rows of SURVEY 8f on the c4 / c3 data (rank 0): rank-1 append vs refactorisation, the inverse-problem
+        # potential (value + gradient for a batch of candidate points), lock-step NUTS transitions
+        if rank == 0:
+            from andvaranaut_b200 import drivers
+            from andvaranaut_b200.priors import ParamSpace
+            from andvaranaut_b200.xpost import InverseLikelihood, XPosterior
+            import scipy.stats as st
+            nrow = {}
+            Na = 8100
+            enga = GPEngine(**cases.engine_args(spec4), device=dev)
+            enga.set_data(X4[:Na], y4[:Na])
+            enga.factorize(th4)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            enga.factorize(th4)
+            torch.cuda.synchronize()
+            t_fact = time.perf_counter() - t0
+            xa, ya = torch.as_tensor(X4[Na:Na + 20], device=dev), torch.as_tensor(y4[Na:Na + 20], device=dev)
+            enga.append(xa[0], ya[0:1])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(1, 20):
+                info_a = enga.append(xa[i], ya[i:i + 1])
+            torch.cuda.synchronize()
+            t_app = (time.perf_counter() - t0) / 19
+            nrow['f3_append'] = {'N': Na, 'append_ms': t_app * 1e3, 'refactorize_ms': t_fact * 1e3, 'info': int(info_a[0]),
+                                 'algorithmic_bytes': 8 * Na * Na,
+                                 'note': 'one new training point, hypers unchanged: avn_gp_append (4 launches, lower triangle '
+                                         'of T read twice = 8 N^2 B) vs avn_gp_factorize of the enlarged set; host-timed incl. the info sync'}
+            pot = InverseLikelihood(enga, lambda x: (x, np.ones_like(x)), np.array([0.3]), 1e-2, 0.0, 0.0)
+            xpost = XPosterior([st.uniform(0, 1)] * 10, pot)
+            zq = np.random.default_rng(7).normal(size=(256, 10))
+            xpost.logp_dlogp(zq, True)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                xpost.logp_dlogp(zq, True)
+            t_inv = (time.perf_counter() - t0) / 3
+            nrow['f4_inverse'] = {'N': enga.N, 'candidates_per_call': 256, 'ms_per_call': t_inv * 1e3,
+                                  'logp_dlogp_evals_per_s': 256 / t_inv,
+                                  'note': 'inverse_opt potential + gradient w.r.t. x for 256 candidate points (restarts / '
+                                          'chains) per call: one avn_gp_predict_grad + host Schur term, host-timed'}
+            del enga, pot, xpost
+            eng3 = GPEngine(**cases.engine_args(spec3), device=dev)
+            eng3.set_data(X3, y3)
+            sp3 = ParamSpace(6, 1, True)
+            post3 = drivers.Posterior(eng3, sp3)
+            z0 = sp3.z_from_theta(th3)
+            t0 = time.perf_counter()
+            tr = drivers.sample(post3, draws=4, tune=4, chains=128, seed=1, start_z=z0[None, :], init_jitter=0.05,
+                                max_treedepth=4)
+            t_nuts = time.perf_counter() - t0
+            nrow['f1_nuts'] = {'chains': 128, 'N': 1000, 'transitions': 8, 'max_treedepth': 4, 'seconds': t_nuts,
+                               'leapfrog_evals': int(post3.n_eval), 'device_calls': int(post3.n_calls),
+                               'evals_per_s': post3.n_eval / t_nuts,
+                               'mean_tree_steps': float(tr.sample_stats['n_steps'].mean()),
+                               'note': 'lock-step NUTS through drivers.sample on the c3 model: every leapfrog of the '
+                                       'still-growing chains is one batched avn_gp_loglik_grad call; host-timed end to end'}
+            del eng3
+            extra['next_rows'] = nrow
         # c5: Bayesian-optimisation iterations through the GPMCMC API (rank 0 only: one sequential optimiser)
         if rank == 0:
             sys.path.insert(0, os.path.join(ROOT, 'tools'))

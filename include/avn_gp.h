@@ -147,7 +147,8 @@ int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const double* Xs_dev,
 
 /* Rank-1 extension of a factorised state by ONE training point with the hyperparameters unchanged: what the data
  * appends of BO / inverse_opt (gpmcmc.py:881-904, :1197-1205) need between two fits when fit_method = 'none' --
- * O(N^2) instead of the O(N^3) refactorisation the reference performs inside every predict call (:588-598).
+ * O(N^2) (four HBM-bound launches, the lower triangle of T read twice) instead of the O(N^3) refactorisation the
+ * reference performs inside every predict call (:588-598).
  * xnew [d] converted inputs, znew [1] converted output (both DEVICE memory).  Works in place on state_dev.
  * Returns 1 (nothing done) when the padded slab is full, N % AVN_TILE == 0: the caller then refactorises with
  * N + 1 points.  info[0] = N + 1 if the new pivot is not positive (state unchanged).  The handle is NOT modified:

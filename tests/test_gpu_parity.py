@@ -394,7 +394,7 @@ def test_rank1_append_equals_refactorisation(name, N0, nadd):
             rmu, rvar = go.predict(spec, th, X[:i + 1], y[:i + 1], Xs)
             assert np.max(np.abs(mu - rmu)) <= 1e-8 * np.max(np.abs(rmu))
             assert np.max(np.abs(var - rvar)) <= 1e-8 * np.max(np.maximum(np.abs(rvar), th[1 + d * nk]))
-    assert eng.N == N0 + nadd and min(launches) == 4      # kxs, V = T k, w = T^T v, append
+    assert eng.N == N0 + nadd and min(launches) == 4      # k, v = T k, w = T^T v, new row
     mu, var = (t.cpu().numpy() for t in eng.predict(Xs))
     rmu, rvar = go.predict(spec, th, X, y, Xs)
     assert np.max(np.abs(mu - rmu)) <= 1e-8 * np.max(np.abs(rmu))
