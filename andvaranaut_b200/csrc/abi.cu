@@ -628,11 +628,23 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
 
 static const int64_t kPanelCols = 148 * 64 * 2;  // test points per K_xs panel
 
+// Small test batches (BO candidates, refine / inverse-problem starts): fewer 64-point column blocks than CTA slots
+// (2 resident CTAs x 148 SMs).  The training rows are then split over blockIdx.y as well -- as many splits as still fit
+// in ONE wave (a second, partly filled wave costs more than it gains: measured) -- and a finish kernel sums the partials
+// in fixed order.  A function of the TOTAL M, so that the result does not depend on how a call is cut into panels.
+static int row_split(int64_t M, int64_t npad) {
+  const int64_t nblk = (M + TILE - 1) / TILE, nb = npad / TILE, slots = 2 * 148;
+  int64_t ns = slots / nblk;
+  if (ns > nb) ns = nb;
+  return (int)(ns < 1 ? 1 : ns);
+}
+
 extern "C" size_t avn_gp_predict_workspace_bytes(const avn_gp* gp, int64_t M) {
   if (!gp || gp->N < 1 || M < 1) return 0;
   const int64_t npad = npad_of(gp->N);
   int64_t cols = align_up(M < kPanelCols ? M : kPanelCols, TILE);
-  return (size_t)(npad * cols * 8);
+  const int64_t ns = row_split(M, npad);
+  return (size_t)((npad + (ns > 1 ? 2 * ns : 0)) * cols * 8);
 }
 
 extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* Xs_dev, int64_t M,
@@ -647,7 +659,8 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   const KernDesc& kd = gp->kd;
   const int64_t npad = npad_of(gp->N);
   StateLayout S = state_layout(gp);
-  const int64_t cols_cap = (int64_t)(ws_bytes / (npad * 8)) / TILE * TILE;
+  const int ns = row_split(M, npad);
+  const int64_t cols_cap = (int64_t)(ws_bytes / ((npad + (ns > 1 ? 2 * ns : 0)) * 8)) / TILE * TILE;
   if (cols_cap < TILE) return fail("avn_gp_predict: workspace too small");
   gp->launches = 0;
   phases_reset(gp);
@@ -669,23 +682,34 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
     const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
     const unsigned nblk = (unsigned)(cols / TILE);
+    double* mu_part = Kxs + npad * cols;           // [ns][cols]   (row-split runs only)
+    double* vpart = mu_part + (int64_t)ns * cols;  // [ns][cols]
     {
       Phase ph(gp, AVN_PH_KXS, st);
-      kxs_kernel<<<nblk, 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols,
-                                              Kxs, out_mean_dev);
+      kxs_kernel<<<dim3(nblk, ns), 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0,
+                                                        (int)cols, Kxs, out_mean_dev, ns, mu_part);
       LAUNCH_CHECK("kxs_kernel");
     }
     Phase ph2(gp, AVN_PH_PREDICT_VAR, st);
-    predict_var_kernel<<<nblk, PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0,
-                                                                         *epi, mean_add_dev, out_mean_dev, out_var_dev);
+    predict_var_kernel<<<dim3(nblk, ns), PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(
+        kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0, *epi, mean_add_dev, out_mean_dev, out_var_dev, ns, vpart);
     LAUNCH_CHECK("predict_var_kernel");
+    if (ns > 1) {
+      predict_finish_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(kd, hyp, ns, mu_part, vpart, (int)cols, M, m0, *epi,
+                                                                           1, mean_add_dev, out_mean_dev, out_var_dev);
+      LAUNCH_CHECK("predict_finish_kernel");
+    }
   }
   return 0;
 }
 
 // ---- predict with gradients w.r.t. the query points (BO refine) -------------------------------------
 extern "C" size_t avn_gp_predict_grad_workspace_bytes(const avn_gp* gp, int64_t M) {
-  return 2 * avn_gp_predict_workspace_bytes(gp, M);
+  if (!gp || gp->N < 1 || M < 1) return 0;
+  const int64_t npad = npad_of(gp->N);
+  int64_t cols = align_up(M < kPanelCols ? M : kPanelCols, TILE);
+  const int64_t ns = row_split(M, npad);
+  return (size_t)((2 * npad + (ns > 1 ? ns * (2 + 2 * gp->kd.d) : 0)) * cols * 8);
 }
 
 extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const double* Xs_dev, int64_t M,
@@ -703,7 +727,9 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
   const KernDesc& kd = gp->kd;
   const int64_t npad = npad_of(gp->N);
   StateLayout S = state_layout(gp);
-  const int64_t cols_cap = (int64_t)(ws_bytes / (2 * npad * 8)) / TILE * TILE;
+  const int ns = row_split(M, npad);
+  const int64_t per_col = 2 * npad + (ns > 1 ? (int64_t)ns * (2 + 2 * kd.d) : 0);
+  const int64_t cols_cap = (int64_t)(ws_bytes / (per_col * 8)) / TILE * TILE;
   if (cols_cap < TILE) return fail("avn_gp_predict_grad: workspace too small");
   gp->launches = 0;
   phases_reset(gp);
@@ -727,28 +753,45 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
     cudaError_t e = opt_in_smem(predict_grad_kernel, smem_pg);
     if (e != cudaSuccess) return fail_cuda("predict_grad_kernel smem", e);
   }
+  avn_epilogue latent = *epi;
+  latent.mode = 0;
   for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
     const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
     const unsigned nblk = (unsigned)(cols / TILE);
     double* Kxs = static_cast<double*>(ws_dev);          // K_xs, later W = K^-1 K_xs
     double* V = Kxs + npad * cols;
+    double* mu_part = V + npad * cols;             // row-split runs only: [ns][cols]
+    double* vpart = mu_part + (int64_t)ns * cols;  // [ns][cols]
+    double* gpart = vpart + (int64_t)ns * cols;    // [ns][cols][2 d]
     {
       Phase ph(gp, AVN_PH_KXS, st);
-      kxs_kernel<<<nblk, 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols,
-                                              Kxs, out_mean_dev);
+      kxs_kernel<<<dim3(nblk, ns), 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0,
+                                                        (int)cols, Kxs, out_mean_dev, ns, mu_part);
       LAUNCH_CHECK("kxs_kernel");
     }
     Phase ph2(gp, AVN_PH_PREDICT_VAR, st);
-    predict_v_kernel<<<nblk, PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0,
-                                                                       pred_noise ? 1 : 0, V, out_var_dev);
+    predict_v_kernel<<<dim3(nblk, ns), PredG::NTHREADS, PredG::SMEM_BYTES, st>>>(
+        kd, (int)npad, hyp, T, Kxs, (int)cols, M, m0, pred_noise ? 1 : 0, V, out_var_dev, ns, vpart);
     LAUNCH_CHECK("predict_v_kernel");
+    if (ns > 1) {
+      predict_finish_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(kd, hyp, ns, mu_part, vpart, (int)cols, M, m0,
+                                                                           latent, pred_noise ? 1 : 0, nullptr,
+                                                                           out_mean_dev, out_var_dev);
+      LAUNCH_CHECK("predict_finish_kernel");
+    }
     ttv_kernel<<<dim3(nblk, (unsigned)(npad / TILE)), TtvG::NTHREADS, TtvG::SMEM_BYTES, st>>>((int)npad, T, V, (int)cols,
                                                                                              Kxs);
     LAUNCH_CHECK("ttv_kernel");
-    predict_grad_kernel<<<nblk, 256, smem_pg, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Kxs, (int)cols, Xs_dev,
-                                                    M, m0, *epi, mean_add_dev, dmean_add_dev, out_mean_dev, out_var_dev,
-                                                    out_dmean_dev, out_dvar_dev);
+    predict_grad_kernel<<<dim3(nblk, ns), 256, smem_pg, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Kxs, (int)cols,
+                                                              Xs_dev, M, m0, *epi, mean_add_dev, dmean_add_dev, out_mean_dev,
+                                                              out_var_dev, out_dmean_dev, out_dvar_dev, ns, gpart);
     LAUNCH_CHECK("predict_grad_kernel");
+    if (ns > 1) {
+      predict_grad_finish_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(
+          kd.d, ns, gpart, (int)cols, M, m0, *epi, mean_add_dev, dmean_add_dev, out_mean_dev, out_var_dev, out_dmean_dev,
+          out_dvar_dev);
+      LAUNCH_CHECK("predict_grad_finish_kernel");
+    }
   }
   return 0;
 }

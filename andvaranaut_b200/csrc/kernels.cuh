@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(256) kxs_kernel(KernDesc kd, int N, int npad, 
                                                   const double* __restrict__ xs_tr, const double* __restrict__ x2_tr,
                                                   const double* __restrict__ alpha, const double* __restrict__ Xtest,
                                                   int64_t M, int64_t m_begin, int mld, double* __restrict__ Kxs,
-                                                  double* __restrict__ mu) {
+                                                  double* __restrict__ mu, int nsplit, double* __restrict__ mu_part) {
   extern __shared__ double smem[];
   __shared__ HypS hyp;
   __shared__ double part[4][TILE];
@@ -625,8 +625,11 @@ __global__ void __launch_bounds__(256) kxs_kernel(KernDesc kd, int N, int npad, 
     }
   }
   __syncthreads();
+  // small test batches: the training rows are split over blockIdx.y (nsplit chunks of whole 64-row blocks)
+  const int nbk = npad / TILE, per = (nbk + nsplit - 1) / nsplit;
+  const int r0 = min(npad, (int)blockIdx.y * per * TILE), r1 = min(npad, r0 + per * TILE);
   double acc = 0.0;
-  for (int n = rg; n < npad; n += 4) {
+  for (int n = r0 + rg; n < r1; n += 4) {
     double v = 0.0;
     if (n < N)
       v = cov_fold(kd, hyp, xs_tr + (int64_t)n * d, (int64_t)npad * d, x2_tr + n, npad, sx + c * ldx, TILE * ldx,
@@ -636,8 +639,56 @@ __global__ void __launch_bounds__(256) kxs_kernel(KernDesc kd, int N, int npad, 
   }
   part[rg][c] = acc;
   __syncthreads();
-  if (tid < TILE && m_begin + col0 + tid < M)
-    mu[m_begin + col0 + tid] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+  if (tid < TILE) {
+    const double sum = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    if (nsplit > 1) mu_part[(int64_t)blockIdx.y * mld + col0 + tid] = sum;
+    else if (m_begin + col0 + tid < M) mu[m_begin + col0 + tid] = sum;
+  }
+}
+
+// Gauss-Hermite reversion / EI / normvar of one point (gpmcmc.py:545-569) from the latent mean and variance
+__device__ __forceinline__ void gh_epilogue(const avn_epilogue& epi, double madd, double& mu, double& var) {
+  if (epi.mode == 0) return;
+  const double sd = sqrt(2.0 * var);
+  double s1 = 0.0, s2 = 0.0;
+  for (int q = 0; q < epi.deg; q++) {
+    double yi = sd * epi.nodes[q] + mu;
+    double yr = prog_rev_const(epi.yrev, yi) + madd;
+    double f = yr;
+    if (epi.mode == 2) {
+      double df = epi.ei_max ? (yr - epi.yopt) : (epi.yopt - yr);
+      f = df > 0.0 ? df : 0.0;
+    }
+    s1 += epi.weights[q] * f;
+    s2 += epi.weights[q] * (yr * yr);
+  }
+  const double ispi = 0.56418958354775628694807945156077;  // 1/sqrt(pi)
+  mu = ispi * s1;
+  var = ispi * s2 - mu * mu;
+  if (epi.normvar) var /= mu * mu;
+}
+
+// row-split runs (nsplit > 1): fixed-order sum of the partial means / column sums of V^2, then the epilogue.
+// grid (cols / 256), one test point per thread.
+__global__ void __launch_bounds__(256) predict_finish_kernel(KernDesc kd, const HypS* __restrict__ hyp_g, int nsplit,
+                                                             const double* __restrict__ mu_part,
+                                                             const double* __restrict__ vpart, int mld, int64_t M,
+                                                             int64_t m_begin, avn_epilogue epi, int pred_noise,
+                                                             const double* __restrict__ mean_add,
+                                                             double* __restrict__ mu_out, double* __restrict__ var_out) {
+  const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x, mg = m_begin + col;
+  if (col >= mld || mg >= M) return;
+  double mu = 0.0, vv = 0.0;
+  for (int s = 0; s < nsplit; s++) {
+    mu += mu_part[(int64_t)s * mld + col];
+    vv += vpart[(int64_t)s * mld + col];
+  }
+  const HypS& hyp = *hyp_g;
+  double var = kdiag_total(kd, hyp) - vv;
+  if (pred_noise) var += hyp.gv;
+  gh_epilogue(epi, mean_add ? mean_add[mg] : 0.0, mu, var);
+  mu_out[mg] = mu;
+  var_out[mg] = var;
 }
 
 using PredG = TileGemm<64, 64, 16, 32, 32, 4, false, true>;
@@ -649,7 +700,8 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc k
                                                                       int64_t M, int64_t m_begin, avn_epilogue epi,
                                                                       const double* __restrict__ mean_add,
                                                                       double* __restrict__ mu_io,
-                                                                      double* __restrict__ var_out) {
+                                                                      double* __restrict__ var_out, int nsplit,
+                                                                      double* __restrict__ vpart) {
   using G = PredG;
   extern __shared__ double smem[];
   __shared__ double colsq[2][TILE];
@@ -659,7 +711,8 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc k
   const int nb = npad / TILE;
   double cs[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   G g;
-  for (int ib = 0; ib < nb; ib++) {
+  // row blocks interleaved over blockIdx.y (cost of block ib is ib + 1 slabs); nsplit == 1: all of them
+  for (int ib = blockIdx.y; ib < nb; ib += nsplit) {
     g.zero();
     g.run(smem, T + (int64_t)ib * TILE * npad, npad, 64, Kxs + col0, mld, 64, (ib + 1) * TILE);
 #pragma unroll
@@ -682,33 +735,17 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc k
     }
   __syncthreads();
   if (tid < TILE) {
+    if (nsplit > 1) {
+      vpart[(int64_t)blockIdx.y * mld + col0 + tid] = colsq[0][tid] + colsq[1][tid];
+      return;
+    }
     const int64_t mg = m_begin + col0 + tid;
     if (mg < M) {
       const HypS& hyp = *hyp_g;
-      double kd_tot = kdiag_total(kd, hyp);
-      double var = kd_tot - (colsq[0][tid] + colsq[1][tid]);
+      double var = kdiag_total(kd, hyp) - (colsq[0][tid] + colsq[1][tid]);
       var += hyp.gv;
       double mu = mu_io[mg];
-      if (epi.mode != 0) {
-        const double madd = mean_add ? mean_add[mg] : 0.0;
-        const double sd = sqrt(2.0 * var);
-        double s1 = 0.0, s2 = 0.0;
-        for (int q = 0; q < epi.deg; q++) {
-          double yi = sd * epi.nodes[q] + mu;
-          double yr = prog_rev_const(epi.yrev, yi) + madd;
-          double f = yr;
-          if (epi.mode == 2) {
-            double df = epi.ei_max ? (yr - epi.yopt) : (epi.yopt - yr);
-            f = df > 0.0 ? df : 0.0;
-          }
-          s1 += epi.weights[q] * f;
-          s2 += epi.weights[q] * (yr * yr);
-        }
-        const double ispi = 0.56418958354775628694807945156077;  // 1/sqrt(pi)
-        mu = ispi * s1;
-        var = ispi * s2 - mu * mu;
-        if (epi.normvar) var /= mu * mu;
-      }
+      gh_epilogue(epi, mean_add ? mean_add[mg] : 0.0, mu, var);
       mu_io[mg] = mu;
       var_out[mg] = var;
     }
@@ -731,7 +768,8 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_v_kernel(KernDesc kd,
                                                                     const double* __restrict__ T,
                                                                     const double* __restrict__ Kxs, int mld, int64_t M,
                                                                     int64_t m_begin, int pred_noise,
-                                                                    double* __restrict__ V, double* __restrict__ var_out) {
+                                                                    double* __restrict__ V, double* __restrict__ var_out,
+                                                                    int nsplit, double* __restrict__ vpart) {
   using G = PredG;
   extern __shared__ double smem[];
   __shared__ double colsq[2][TILE];
@@ -741,7 +779,7 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_v_kernel(KernDesc kd,
   const int nb = npad / TILE;
   double cs[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   G g;
-  for (int ib = 0; ib < nb; ib++) {
+  for (int ib = blockIdx.y; ib < nb; ib += nsplit) {
     g.zero();
     g.run(smem, T + (int64_t)ib * TILE * npad, npad, 64, Kxs + col0, mld, 64, (ib + 1) * TILE);
 #pragma unroll
@@ -766,6 +804,10 @@ __global__ void __launch_bounds__(PredG::NTHREADS) predict_v_kernel(KernDesc kd,
     }
   __syncthreads();
   if (tid < TILE) {
+    if (nsplit > 1) {
+      vpart[(int64_t)blockIdx.y * mld + col0 + tid] = colsq[0][tid] + colsq[1][tid];
+      return;
+    }
     const int64_t mg = m_begin + col0 + tid;
     if (mg < M) {
       const HypS& hyp = *hyp_g;
@@ -800,95 +842,14 @@ __global__ void __launch_bounds__(TtvG::NTHREADS) ttv_kernel(int npad, const dou
     }
 }
 
-// grid (column blocks), 256 threads = 4 row groups x 64 test points.
-__global__ void __launch_bounds__(256) predict_grad_kernel(KernDesc kd, int N, int npad, const HypS* __restrict__ hyp_g,
-                                                           const double* __restrict__ xs_tr,
-                                                           const double* __restrict__ x2_tr,
-                                                           const double* __restrict__ alpha,
-                                                           const double* __restrict__ Wm, int mld,
-                                                           const double* __restrict__ Xtest, int64_t M, int64_t m_begin,
-                                                           avn_epilogue epi, const double* __restrict__ mean_add,
-                                                           const double* __restrict__ dmean_add,
-                                                           double* __restrict__ mu_io, double* __restrict__ var_io,
-                                                           double* __restrict__ dmean_out, double* __restrict__ dvar_out) {
-  extern __shared__ double smem[];
-  __shared__ HypS hyp;
-  const int tid = threadIdx.x, c = tid & 63, rg = tid >> 6;
-  const int d = kd.d, nk = kd.nkern;
-  const int64_t col0 = (int64_t)blockIdx.x * TILE;
-  const int64_t mg = m_begin + col0 + c;
-  for (int e = tid; e < (int)(sizeof(HypS) / sizeof(double)); e += 256)
-    reinterpret_cast<double*>(&hyp)[e] = reinterpret_cast<const double*>(hyp_g)[e];
-  __syncthreads();
-  const int ldx = d | 1;
-  double* sx = smem;                       // [nk][64][ldx] scaled test points
-  double* sx2 = sx + nk * TILE * ldx;      // [nk][64]
-  double* sred = sx2 + nk * TILE;          // [4][64][2 * d] partial sums of the row groups
-  if (rg == 0) {
-    for (int k = 0; k < nk; k++) {
-      double tmp[MAXD];
-      for (int m = 0; m < d; m++) {
-        const double x = (mg < M) ? Xtest[mg * d + m] : 0.0;
-        tmp[m] = __dmul_rn(x, hyp.invl[k][m]);
-        sx[(k * TILE + c) * ldx + m] = tmp[m];
-      }
-      sx2[k * TILE + c] = sumsq_numpy_order(tmp, d);
-    }
-  }
-  __syncthreads();
-  double gmu[MAXD], gs[MAXD];
-#pragma unroll
-  for (int m = 0; m < MAXD; m++) gmu[m] = gs[m] = 0.0;
-  for (int n = rg; n < N; n += 4) {
-    // kernel values / derivatives of every kernel of the fold at the pair (train n, test c)
-    double vals[MAXK], dks[MAXK];
-    for (int q = 0; q < nk; q++) {
-      const double r2 = sqdist_gram(xs_tr + ((int64_t)q * npad + n) * d, sx + (q * TILE + c) * ldx,
-                                    x2_tr[(int64_t)q * npad + n], sx2[q * TILE + c], d);
-      double kq, dkq;
-      kern_val(kd.kern[q], r2, hyp.alpha, kq, dkq);
-      vals[q] = hyp.kv[q] * kq;
-      dks[q] = (r2 > 0.0) ? hyp.kv[q] * dkq : 0.0;   // the clip of square_dist has zero slope where it is active
-    }
-    // coef[q] = d fold / d vals[q] through the left-to-right fold (as in kinv_grad_kernel)
-    double coef[MAXK];
-    {
-      double prefs[MAXK];
-      prefs[0] = vals[0];
-      for (int q = 1; q < nk; q++) prefs[q] = (kd.op[q - 1] == AVN_ADD) ? prefs[q - 1] + vals[q] : prefs[q - 1] * vals[q];
-      double gg = 1.0;
-      for (int q = nk - 1; q >= 1; q--) {
-        if (kd.op[q - 1] == AVN_ADD) {
-          coef[q] = gg;
-        } else {
-          coef[q] = gg * prefs[q - 1];
-          gg *= vals[q];
-        }
-      }
-      coef[0] = gg;
-    }
-    const double an = alpha[n], wn_ = Wm[(int64_t)n * mld + col0 + c];
-    for (int q = 0; q < nk; q++) {
-      const double f = 2.0 * coef[q] * dks[q];
-      const double* xr = xs_tr + ((int64_t)q * npad + n) * d;
-      const double* xc = sx + (q * TILE + c) * ldx;
-#pragma unroll
-      for (int m = 0; m < MAXD; m++)
-        if (m < d) {
-          const double dk = f * (xc[m] - xr[m]) * hyp.invl[q][m];
-          gmu[m] = fma(an, dk, gmu[m]);
-          gs[m] = fma(wn_, dk, gs[m]);
-        }
-    }
-  }
-#pragma unroll
-  for (int m = 0; m < MAXD; m++)
-    if (m < d) {
-      sred[((rg * TILE + c) * 2 + 0) * d + m] = gmu[m];
-      sred[((rg * TILE + c) * 2 + 1) * d + m] = gs[m];
-    }
-  __syncthreads();
-  if (tid >= TILE || mg >= M) return;
+// chain rule of the reversion epilogue for one point: latent (mu, var) and the raw contractions
+// g1[m] = sum_n alpha_n dk_n/dx_m, g2[m] = sum_n w_n dk_n/dx_m  ->  outputs and their gradients
+__device__ __forceinline__ void grad_epilogue(const avn_epilogue& epi, int d, int64_t mg,
+                                              const double* __restrict__ mean_add,
+                                              const double* __restrict__ dmean_add, const double* g1v,
+                                              const double* g2v, double* __restrict__ mu_io,
+                                              double* __restrict__ var_io, double* __restrict__ dmean_out,
+                                              double* __restrict__ dvar_out) {
   double mu = mu_io[mg], var = var_io[mg];
   // outputs (om, ov) as functions of the latent (mu, var): partial derivatives a* = d om, b* = d ov
   double am = 1.0, av = 0.0, bm = 0.0, bv = 1.0, cm = 0.0, cv = 0.0;   // c*: factor of d mean_add / d x
@@ -937,18 +898,148 @@ __global__ void __launch_bounds__(256) predict_grad_kernel(KernDesc kd, int N, i
   mu_io[mg] = mu;
   var_io[mg] = var;
   for (int m = 0; m < d; m++) {
-    double g1 = 0.0, g2 = 0.0;
-    for (int r = 0; r < 4; r++) {
-      g1 += sred[((r * TILE + c) * 2 + 0) * d + m];
-      g2 += sred[((r * TILE + c) * 2 + 1) * d + m];
-    }
-    g2 *= -2.0;   // d var / d x_m
+    const double g1 = g1v[m], g2 = -2.0 * g2v[m];   // g2: d var / d x_m
     const double dm_add = dmean_add ? dmean_add[mg * d + m] : 0.0;
     dmean_out[mg * d + m] = am * g1 + av * g2 + cm * dm_add;
     dvar_out[mg * d + m] = bm * g1 + bv * g2 + cv * dm_add;
   }
 }
 
+// grid (column blocks, nsplit), 256 threads = 4 row groups x 64 test points.  nsplit > 1 (small test batches): the
+// training rows are split over blockIdx.y, the CTA stores its partial contractions and predict_grad_finish_kernel
+// runs the epilogue.
+__global__ void __launch_bounds__(256) predict_grad_kernel(KernDesc kd, int N, int npad, const HypS* __restrict__ hyp_g,
+                                                           const double* __restrict__ xs_tr,
+                                                           const double* __restrict__ x2_tr,
+                                                           const double* __restrict__ alpha,
+                                                           const double* __restrict__ Wm, int mld,
+                                                           const double* __restrict__ Xtest, int64_t M, int64_t m_begin,
+                                                           avn_epilogue epi, const double* __restrict__ mean_add,
+                                                           const double* __restrict__ dmean_add,
+                                                           double* __restrict__ mu_io, double* __restrict__ var_io,
+                                                           double* __restrict__ dmean_out, double* __restrict__ dvar_out,
+                                                           int nsplit, double* __restrict__ gpart) {
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  const int tid = threadIdx.x, c = tid & 63, rg = tid >> 6;
+  const int d = kd.d, nk = kd.nkern;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int64_t mg = m_begin + col0 + c;
+  for (int e = tid; e < (int)(sizeof(HypS) / sizeof(double)); e += 256)
+    reinterpret_cast<double*>(&hyp)[e] = reinterpret_cast<const double*>(hyp_g)[e];
+  __syncthreads();
+  const int ldx = d | 1;
+  double* sx = smem;                       // [nk][64][ldx] scaled test points
+  double* sx2 = sx + nk * TILE * ldx;      // [nk][64]
+  double* sred = sx2 + nk * TILE;          // [4][64][2 * d] partial sums of the row groups
+  if (rg == 0) {
+    for (int k = 0; k < nk; k++) {
+      double tmp[MAXD];
+      for (int m = 0; m < d; m++) {
+        const double x = (mg < M) ? Xtest[mg * d + m] : 0.0;
+        tmp[m] = __dmul_rn(x, hyp.invl[k][m]);
+        sx[(k * TILE + c) * ldx + m] = tmp[m];
+      }
+      sx2[k * TILE + c] = sumsq_numpy_order(tmp, d);
+    }
+  }
+  __syncthreads();
+  double gmu[MAXD], gs[MAXD];
+#pragma unroll
+  for (int m = 0; m < MAXD; m++) gmu[m] = gs[m] = 0.0;
+  const int nbk = npad / TILE, per = (nbk + nsplit - 1) / nsplit;
+  const int r0 = min(N, (int)blockIdx.y * per * TILE), r1 = min(N, r0 + per * TILE);
+  for (int n = r0 + rg; n < r1; n += 4) {
+    // kernel values / derivatives of every kernel of the fold at the pair (train n, test c)
+    double vals[MAXK], dks[MAXK];
+    for (int q = 0; q < nk; q++) {
+      const double r2 = sqdist_gram(xs_tr + ((int64_t)q * npad + n) * d, sx + (q * TILE + c) * ldx,
+                                    x2_tr[(int64_t)q * npad + n], sx2[q * TILE + c], d);
+      double kq, dkq;
+      kern_val(kd.kern[q], r2, hyp.alpha, kq, dkq);
+      vals[q] = hyp.kv[q] * kq;
+      dks[q] = (r2 > 0.0) ? hyp.kv[q] * dkq : 0.0;   // the clip of square_dist has zero slope where it is active
+    }
+    // coef[q] = d fold / d vals[q] through the left-to-right fold (as in kinv_grad_kernel)
+    double coef[MAXK];
+    {
+      double prefs[MAXK];
+      prefs[0] = vals[0];
+      for (int q = 1; q < nk; q++) prefs[q] = (kd.op[q - 1] == AVN_ADD) ? prefs[q - 1] + vals[q] : prefs[q - 1] * vals[q];
+      double gg = 1.0;
+      for (int q = nk - 1; q >= 1; q--) {
+        if (kd.op[q - 1] == AVN_ADD) {
+          coef[q] = gg;
+        } else {
+          coef[q] = gg * prefs[q - 1];
+          gg *= vals[q];
+        }
+      }
+      coef[0] = gg;
+    }
+    const double an = alpha[n], wn_ = Wm[(int64_t)n * mld + col0 + c];
+    for (int q = 0; q < nk; q++) {
+      const double f = 2.0 * coef[q] * dks[q];
+      const double* xr = xs_tr + ((int64_t)q * npad + n) * d;
+      const double* xc = sx + (q * TILE + c) * ldx;
+#pragma unroll
+      for (int m = 0; m < MAXD; m++)
+        if (m < d) {
+          const double dk = f * (xc[m] - xr[m]) * hyp.invl[q][m];
+          gmu[m] = fma(an, dk, gmu[m]);
+          gs[m] = fma(wn_, dk, gs[m]);
+        }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MAXD; m++)
+    if (m < d) {
+      sred[((rg * TILE + c) * 2 + 0) * d + m] = gmu[m];
+      sred[((rg * TILE + c) * 2 + 1) * d + m] = gs[m];
+    }
+  __syncthreads();
+  if (tid >= TILE) return;
+  double g1[MAXD], g2[MAXD];
+  for (int m = 0; m < d; m++) {
+    g1[m] = g2[m] = 0.0;
+    for (int r = 0; r < 4; r++) {
+      g1[m] += sred[((r * TILE + c) * 2 + 0) * d + m];
+      g2[m] += sred[((r * TILE + c) * 2 + 1) * d + m];
+    }
+  }
+  if (nsplit > 1) {
+    double* gp = gpart + ((int64_t)blockIdx.y * mld + col0 + c) * 2 * d;
+    for (int m = 0; m < d; m++) {
+      gp[m] = g1[m];
+      gp[d + m] = g2[m];
+    }
+    return;
+  }
+  if (mg >= M) return;
+  grad_epilogue(epi, d, mg, mean_add, dmean_add, g1, g2, mu_io, var_io, dmean_out, dvar_out);
+}
+
+// grid (cols / 128), one test point per thread: fixed-order sum of the row-split partials, then the epilogue.
+__global__ void __launch_bounds__(128) predict_grad_finish_kernel(int d, int nsplit, const double* __restrict__ gpart,
+                                                                  int mld, int64_t M, int64_t m_begin, avn_epilogue epi,
+                                                                  const double* __restrict__ mean_add,
+                                                                  const double* __restrict__ dmean_add,
+                                                                  double* __restrict__ mu_io, double* __restrict__ var_io,
+                                                                  double* __restrict__ dmean_out,
+                                                                  double* __restrict__ dvar_out) {
+  const int64_t col = (int64_t)blockIdx.x * 128 + threadIdx.x, mg = m_begin + col;
+  if (col >= mld || mg >= M) return;
+  double g1[MAXD], g2[MAXD];
+  for (int m = 0; m < d; m++) g1[m] = g2[m] = 0.0;
+  for (int s = 0; s < nsplit; s++) {
+    const double* gp = gpart + ((int64_t)s * mld + col) * 2 * d;
+    for (int m = 0; m < d; m++) {
+      g1[m] += gp[m];
+      g2[m] += gp[d + m];
+    }
+  }
+  grad_epilogue(epi, d, mg, mean_add, dmean_add, g1, g2, mu_io, var_io, dmean_out, dvar_out);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Rank-1 extension of a factorised state by ONE training point, hyperparameters unchanged (the data

@@ -287,6 +287,12 @@ class GPEngine:
             e.yrev = _lib.make_prog(yrev, nparams=0)
         return e
 
+    @staticmethod
+    def _one_tile_bytes(full, M):
+        """smallest usable predict workspace: one 64-point column block (the library's size is linear in the panel width)"""
+        cols = min((M + _lib.AVN_TILE - 1) // _lib.AVN_TILE * _lib.AVN_TILE, 148 * 64 * 2)
+        return full // cols * _lib.AVN_TILE
+
     def predict(self, Xs, epilogue=None, mean_add=None, max_ws_bytes=4 << 30):
         """Xs [M,nx] converted test points -> (mean [M], var [M]) device tensors."""
         if self._state is None:
@@ -296,8 +302,8 @@ class GPEngine:
         if Xs.ndim != 2 or Xs.shape[1] != self.nx:
             raise ValueError('Xs must be [M,nx]')
         epi = epilogue if epilogue is not None else self.make_epilogue()
-        need = min(self.lib.avn_gp_predict_workspace_bytes(self._h, M), max_ws_bytes)
-        need = max(need, self.npad * 64 * 8)
+        full = self.lib.avn_gp_predict_workspace_bytes(self._h, M)
+        need = max(min(full, max_ws_bytes), self._one_tile_bytes(full, M))
         if self._pws is None or self._pws.numel() < need:
             self._pws = None
             self._pws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -322,8 +328,8 @@ class GPEngine:
             raise ValueError('Xs must be [M,nx]')
         M = Xs.shape[0]
         epi = epilogue if epilogue is not None else self.make_epilogue()
-        need = min(self.lib.avn_gp_predict_grad_workspace_bytes(self._h, M), max_ws_bytes)
-        need = max(need, 2 * self.npad * 64 * 8)
+        full = self.lib.avn_gp_predict_grad_workspace_bytes(self._h, M)
+        need = max(min(full, max_ws_bytes), self._one_tile_bytes(full, M))
         if self._pws is None or self._pws.numel() < need:
             self._pws = None
             self._pws = torch.empty(need, dtype=torch.uint8, device=self.device)
