@@ -59,11 +59,14 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
   load_hyp(hyp, kd, theta + (int64_t)b * kd.P);
   G g;
   g.zero();
+  // the wm = 1 warps skip half of the first slab: alternate which hardware warps (SM sub-partitions) those are
+  const int swz = (int)((blockIdx.x * 2654435761u) >> 16) & 1;   // a function of the tile only: batch-size independent results
+  g.swz = swz;
   // rows >= N of T are those of the identity: the k range stops at N rounded up to the slab depth, and the
   // padding rows of the last block row issue no DMMA
   // first slab: A = T[i,i] is lower triangular, its columns m >= 32 vanish for the first 32 k
   g.run(smem, T + (int64_t)i0 * npad + i0, npad, min(TILE, N - i0), T + (int64_t)i0 * npad + j0, npad, 64,
-        min(npad, (N + G::BK - 1) / G::BK * G::BK) - i0, [](int) {}, ((threadIdx.x >> 5) % G::WARPS_M) == 1 ? 32 / G::BK : 0);
+        min(npad, (N + G::BK - 1) / G::BK * G::BK) - i0, [](int) {}, (((threadIdx.x >> 5) ^ swz) % G::WARPS_M) == 1 ? 32 / G::BK : 0);
 
   // ---- stage the small operands (the pipeline buffers are free after run()) ----
   const KinvFastLayout lay(d);
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
   for (int e = tid; e < 4 * MAXACC; e += G::NTHREADS) (&wpart[0][0])[e] = 0.0;
   __syncthreads();
 
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = (tid >> 5) ^ swz, lane = tid & 31;
   const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
   const double symw = (ti == tj) ? 1.0 : 2.0;
 

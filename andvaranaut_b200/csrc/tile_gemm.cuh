@@ -84,6 +84,9 @@ struct TileGemm {
   static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * sizeof(double);
 
   double acc[MI][NI][2];
+  // warp-id swizzle (0 or 1): which hardware warps (= SM sub-partitions) play the wm = 0 / wm = 1 roles.  Callers whose
+  // wm = 1 warps skip work (triangular first slabs) alternate it between CTAs so that no sub-partition idles.
+  int swz = 0;
 
   __device__ __forceinline__ void zero() {
 #pragma unroll
@@ -135,7 +138,7 @@ struct TileGemm {
   __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda, int a_rows, const double* Bpt,
                                       int64_t ldb, int b_rows, int klen, PreIssue pre_issue, int skip_kt = 0) {
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = (tid >> 5) ^ swz, lane = tid & 31;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int g = lane >> 2, t = lane & 3;
     const int KT = klen / BK;
@@ -189,7 +192,7 @@ struct TileGemm {
   // Visit every accumulator element: f(row_in_tile, col_in_tile, value&)
   template <typename F>
   __device__ __forceinline__ void for_each(F f) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (threadIdx.x >> 5) ^ swz, lane = threadIdx.x & 31;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
