@@ -40,45 +40,65 @@ def lhc(n, d, seed):
     return qmc.LatinHypercube(d=d, seed=seed).random(n)
 
 
+class Workload(tuple):
+    """(engine kwargs, X, y, theta) of one synthetic configuration.  Only package code builds it: the GPU arm never
+    touches ``oracle/``; ``oracle_spec(name)`` gives the CPU legs the oracle's description of the same model."""
+    __slots__ = ()
+
+
+def _warp_programs(d):
+    import scipy.stats as st
+    from andvaranaut_b200 import transform as T
+    xw = [T.wgp(['uniform', 'kumaraswamy'], np.ones(2), y=np.linspace(0.1, 0.9, 8), xdist=st.uniform(0.0, 1.0)).program()
+          for _ in range(d)]
+    yw = T.wgp(['logarithm', 'sal', 'meanstd'], np.ones(4), y=np.linspace(0.5, 1.5, 8)).program()
+    return xw, yw
+
+
 def workload_c2(seed=202, N=2000, d=8):
-    from oracle.gp_oracle import ModelSpec
     rng = np.random.default_rng(seed)
     X = lhc(N, d, seed)
     a = np.linspace(0.5, 2.0, d)
     y = np.exp(np.sum(np.sin(2 * np.pi * a * X), axis=1) / d + 0.5 * X[:, 0] * X[:, 1]) + 0.01 * rng.normal(size=N)
-    spec = ModelSpec(nx=d, kerns=['Matern52'], noise=True,
-                     xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * d, ywarp=['logarithm', 'sal', 'meanstd'])
-    o = spec.offsets()
-    th = np.zeros(o['P'])
-    th[o['gv']] = 1e-4
-    th[o['l']:o['l'] + d] = 0.7
-    th[o['kv']] = 1.5
-    th[o['iw']:o['iw'] + 2 * d] = 1.0
-    th[o['cw']:o['cw'] + 4] = [0.0, 1.0, 0.0, 1.0]
-    return spec, X, y, th
+    xw, yw = _warp_programs(d)
+    kw = dict(nx=d, kerns=['Matern52'], ops=[], noise=True, jitter=1e-6, xwarps=xw, ywarp=yw)
+    # theta layout: [gv][l: d][kv][iwgp: 2 d][cwgp: 4]
+    th = np.concatenate([[1e-4], 0.7 * np.ones(d), [1.5], np.ones(2 * d), [0.0, 1.0, 0.0, 1.0]])
+    return Workload((kw, X, y, th))
 
 
 def workload_c3(seed=303, N=1000, d=6):
-    from oracle.gp_oracle import ModelSpec
     rng = np.random.default_rng(seed)
     X = lhc(N, d, seed)
     a = np.linspace(0.5, 2.0, d)
     y = np.sum(np.sin(2 * np.pi * a * X), axis=1) + 0.05 * rng.normal(size=N)
     y = (y - y.mean()) / y.std()
-    spec = ModelSpec(nx=d, kerns=['RBF'], noise=True)
+    kw = dict(nx=d, kerns=['RBF'], ops=[], noise=True, jitter=1e-6)
     th = np.concatenate([[2e-3], 0.6 * np.ones(d), [1.5]])
-    return spec, X, y, th
+    return Workload((kw, X, y, th))
 
 
 def workload_c4(seed=404, N=8192, d=10):
-    from oracle.gp_oracle import ModelSpec
     rng = np.random.default_rng(seed)
     X = lhc(N, d, seed)
     y = np.sin(X @ np.linspace(0.5, 2.0, d)) + 0.01 * rng.normal(size=N)
     y = (y - y.mean()) / y.std()
-    spec = ModelSpec(nx=d, kerns=['Matern52'], noise=True)
+    kw = dict(nx=d, kerns=['Matern52'], ops=[], noise=True, jitter=1e-6)
     th = np.concatenate([[1e-4], np.ones(d), [1.5]])
-    return spec, X, y, th
+    return Workload((kw, X, y, th))
+
+
+def oracle_spec(name):
+    """the oracle's description of workload ``name`` (CPU baseline / reference legs only)."""
+    from oracle.gp_oracle import ModelSpec
+    if name == 'c2':
+        return ModelSpec(nx=8, kerns=['Matern52'], noise=True, xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * 8,
+                         ywarp=['logarithm', 'sal', 'meanstd'])
+    if name == 'c3':
+        return ModelSpec(nx=6, kerns=['RBF'], noise=True)
+    if name == 'c4':
+        return ModelSpec(nx=10, kerns=['Matern52'], noise=True)
+    raise ValueError(name)
 
 
 def theta_cloud(th, B, seed, scale=0.1):
@@ -187,7 +207,8 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import gp_oracle as go
-    spec, X, y, th = workload_c2()
+    _, X, y, th = workload_c2()
+    spec = oracle_spec('c2')
     thetas = theta_cloud(th, max(args.steps + args.warmup, 4), seed=202)
     cores, api = blas_threads()
     per_step = 1  # one evaluation per step: ~1-2 s of multi-threaded LAPACK at N=2000
@@ -232,7 +253,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import cases
     from andvaranaut_b200.gp import GPEngine
 
     rank = int(os.environ.get('RANK', '0'))
@@ -273,10 +293,10 @@ def main():
     p64 = dgemm_peak()
 
     # ---- headline: c2 batched loglik+grad ----------------------------------------------------------
-    spec, X, y, th = workload_c2()
+    kw2, X, y, th = workload_c2()
     N, d, P = X.shape[0], X.shape[1], len(th)
     B = args.batch
-    eng = GPEngine(**cases.engine_args(spec), device=dev)
+    eng = GPEngine(**kw2, device=dev)
     eng.set_data(X, y)
     eng.set_streams(args.streams)
     thetas = theta_cloud(th, B * world, seed=202)[rank * B:(rank + 1) * B]
@@ -379,9 +399,9 @@ def main():
     extra = {}
     if not args.no_extra:
         # c3: 512 chains x N=1000, d=6, sharded over the ranks (strong scaling by definition of the config)
-        spec3, X3, y3, th3 = workload_c3()
+        kw3, X3, y3, th3 = workload_c3()
         B3 = 512 // world
-        eng3 = GPEngine(**cases.engine_args(spec3), device=dev)
+        eng3 = GPEngine(**kw3, device=dev)
         eng3.set_data(X3, y3)
         eng3.set_streams(args.streams)
         t3 = torch.as_tensor(theta_cloud(th3, 512, seed=303)[rank * B3:(rank + 1) * B3], device=dev)
@@ -402,8 +422,8 @@ def main():
                                    'nonpd': int((o3[2] != 0).sum())}
         del eng3
         # c4: predict pts/s, N=8192 d=10, test blocks sharded (weak: M_sub points per GPU per step)
-        spec4, X4, y4, th4 = workload_c4()
-        eng4 = GPEngine(**cases.engine_args(spec4), device=dev)
+        kw4, X4, y4, th4 = workload_c4()
+        eng4 = GPEngine(**kw4, device=dev)
         eng4.set_data(X4, y4)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng4.factorize(th4)
@@ -438,6 +458,7 @@ def main():
             # which refactorises and recompiles on every call), 2 blocks of 4096 points, vectorised GH epilogue;
             # plus the reference's literal per-point GH loop (gpmcmc.py:549-563) on 10^4 points
             from oracle import gp_oracle as go
+            spec4 = oracle_spec('c4')
             cores, api = blas_threads()
             t0 = time.perf_counter()
             _, _, L4 = go.predict_blocked(spec4, th4, X4, y4, X4[:8], block=8)
@@ -464,7 +485,7 @@ def main():
             import scipy.stats as st
             nrow = {}
             Na = 8100
-            enga = GPEngine(**cases.engine_args(spec4), device=dev)
+            enga = GPEngine(**kw4, device=dev)
             enga.set_data(X4[:Na], y4[:Na])
             enga.factorize(th4)
             torch.cuda.synchronize()
@@ -497,7 +518,7 @@ def main():
                                   'note': 'inverse_opt potential + gradient w.r.t. x for 256 candidate points (restarts / '
                                           'chains) per call: one avn_gp_predict_grad + host Schur term, host-timed'}
             del enga, pot, xpost
-            eng3 = GPEngine(**cases.engine_args(spec3), device=dev)
+            eng3 = GPEngine(**kw3, device=dev)
             eng3.set_data(X3, y3)
             sp3 = ParamSpace(6, 1, True)
             post3 = drivers.Posterior(eng3, sp3)
@@ -526,6 +547,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import gp_oracle as go
+        spec = oracle_spec('c2')
         r0 = go.loglik(spec, th, X, y, want_grad=False, keep=True)
         sv = np.linalg.svd(r0.L, compute_uv=False)
         line['config']['cond_K_nominal_theta'] = float((sv[0] / sv[-1]) ** 2)

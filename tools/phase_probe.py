@@ -9,16 +9,14 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import bench  # noqa: E402
-import cases  # noqa: E402
 from andvaranaut_b200.gp import GPEngine  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else 'c2'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 grad = (sys.argv[3] != 'nograd') if len(sys.argv) > 3 else True
-spec, X, y, th = getattr(bench, 'workload_' + wl)()
-eng = GPEngine(**cases.engine_args(spec), device='cuda:0')
+kw, X, y, th = getattr(bench, 'workload_' + wl)()
+eng = GPEngine(**kw, device='cuda:0')
 eng.set_data(X, y)
 thetas = torch.as_tensor(bench.theta_cloud(th, B, seed=1), device='cuda:0')
 for _ in range(3):
