@@ -90,23 +90,32 @@ class InverseLikelihood:
         mu, s, dmu, ds = (t.cpu().numpy() for t in self.engine.predict_grad(xc, pred_noise=False))
         s = s + self.c_shift
         nobs = len(self.yo)
-        one = np.ones(nobs)
-        S = s[:, None, None] * np.ones((nobs, nobs)) + np.diag(self.noise_o)[None, :, :]
+        B = len(x)
         e = self.yo[None, :] - mu[:, None]
-        val = np.full(len(x), -np.inf)
-        gmu = np.zeros(len(x))
-        gs = np.zeros(len(x))
-        for b in range(len(x)):           # nobs x nobs systems, nobs is 1 in the reference's own use
-            if not np.all(np.isfinite(S[b])):
-                continue
-            try:
-                Lb = np.linalg.cholesky(S[b])
-            except np.linalg.LinAlgError:
-                continue
-            u = np.linalg.solve(Lb, np.stack([e[b], one], axis=1))
-            Se, S1 = np.linalg.solve(Lb.T, u).T
-            val[b] = self.const - 0.5 * np.dot(e[b], Se) - np.sum(np.log(np.diag(Lb))) - nobs * HALF_LOG_2PI
-            gmu[b] = np.sum(Se)
-            gs[b] = 0.5 * (np.sum(Se) ** 2 - np.sum(S1))
+        val = np.full(B, -np.inf)
+        gmu = np.zeros(B)
+        gs = np.zeros(B)
+        # S = s 11^T + D_o per candidate (nobs x nobs, nobs is 1 in the reference's own use): batched Cholesky of the
+        # candidates whose S is finite with positive pivots; the others keep logp = -inf
+        S = s[:, None, None] * np.ones((nobs, nobs)) + np.diag(self.noise_o)[None, :, :]
+        ok = np.isfinite(S).all(axis=(1, 2)) & np.isfinite(e).all(axis=1)
+        if nobs == 1:
+            ok &= np.where(ok, S[:, 0, 0], 0.0) > 0.0
+            d0 = S[ok, 0, 0]
+            Se, S1 = e[ok, 0] / d0, 1.0 / d0
+            val[ok] = self.const - 0.5 * e[ok, 0] * Se - 0.5 * np.log(d0) - HALF_LOG_2PI
+            gmu[ok] = Se
+            gs[ok] = 0.5 * (Se ** 2 - S1)
+        else:
+            for b in np.where(ok)[0]:
+                try:
+                    Lb = np.linalg.cholesky(S[b])
+                except np.linalg.LinAlgError:
+                    continue
+                u = np.linalg.solve(Lb, np.stack([e[b], np.ones(nobs)], axis=1))
+                Se, S1 = np.linalg.solve(Lb.T, u).T
+                val[b] = self.const - 0.5 * np.dot(e[b], Se) - np.sum(np.log(np.diag(Lb))) - nobs * HALF_LOG_2PI
+                gmu[b] = np.sum(Se)
+                gs[b] = 0.5 * (np.sum(Se) ** 2 - np.sum(S1))
         gx = (gmu[:, None] * dmu + gs[:, None] * ds) * dc
         return val, gx
