@@ -322,8 +322,8 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   fa.prof = nullptr;
 #ifdef AVN_FACTOR_PROF
   static long long* prof_dev = nullptr;
-  if (!prof_dev) cudaMalloc(&prof_dev, 64);
-  cudaMemsetAsync(prof_dev, 0, 64, st);
+  if (!prof_dev) cudaMalloc(&prof_dev, 128);
+  cudaMemsetAsync(prof_dev, 0, 128, st);
   fa.prof = prof_dev;
 #endif
   {
@@ -333,13 +333,21 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   }
 #ifdef AVN_FACTOR_PROF
   {
-    long long h[8];
-    cudaMemcpyAsync(h, prof_dev, 64, cudaMemcpyDeviceToHost, st);
+    long long h[16];
+    cudaMemcpyAsync(h, prof_dev, 128, cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     double tot = 0;
     for (int q = 0; q < 6; q++) tot += (double)h[q];
     fprintf(stderr, "[factor prof] grid %d  ticket %.1f%%  wait %.1f%%  gemm %.1f%%  wait_tkk %.1f%%  epilogue %.1f%%  diag %.1f%%  (cycles/CTA %.0f)\n",
             grid, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / grid);
+    const double ntask_pr = (double)B * nb * (nb - 1) / 2 * (want_inverse ? 2 : 1);
+    fprintf(stderr, "[factor prof] per task: diag %.0f cycles (x %d D tasks per sample), P/R epilogue %.0f cycles, P/R gemm %.0f cycles\n",
+            (double)h[5] / ((double)B * nb), nb, (double)h[4] / ntask_pr, (double)h[2] / ntask_pr);
+    fprintf(stderr, "[factor prof] diag fn (thread 0 cycles per D task): warp elimination %.0f, store %.0f, trsm %.0f, syrk %.0f, T off-diagonal %.0f\n",
+            (double)h[8] / ((double)B * nb), (double)h[9] / ((double)B * nb), (double)h[10] / ((double)B * nb),
+            (double)h[11] / ((double)B * nb), (double)h[12] / ((double)B * nb));
+    fprintf(stderr, "[factor prof] D task: stage %.0f cycles, chol+inverse %.0f cycles, store+publish %.0f cycles\n",
+            (double)h[7] / ((double)B * nb), (double)h[6] / ((double)B * nb), (double)h[5] / ((double)B * nb));
   }
 #endif
   return 0;

@@ -199,151 +199,202 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64 x 64 diagonal block: Cholesky AND triangular inverse in one sweep, 128 threads, one barrier per column.
-// Elimination on [A | I] in place: L^-1 [A | I] = [L^T | L^-1].  The lower triangle is held in registers as a
-// 16 x 16 grid of 4 x 4 sub-blocks; thread (ty, tx), ty in 0..7, owns the sub-blocks (ty, tx) and (ty + 8, tx).
-// Before step j an entry (i, c) holds the partially eliminated A value if c >= j and the partially formed
-// T = L^-1 value if c < j.  Step j: the owners have published column j of A and row j of the T part in
-// vec[j & 1]; after the barrier every thread forms inv = 1/sqrt(A_jj) itself, then
-//   l_i = A_ij inv (saved to shared memory: column j of L),   T_jc = T_jc inv (c < j),   T_jj = inv,
-//   rows i > j:   A_ic -= l_i l_c (j < c <= i),   T_ic -= l_i T_jc (c < j),   T_ij = -l_i inv,
-// and the owners of column / row j+1 publish them for the next step.  64 dependent steps in all (the earlier
-// two-sweep version needed 128) and half the FP64 work per step.
-// sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T.
+// 64 x 64 diagonal block: Cholesky AND triangular inverse, four 16-wide panels, 128 threads.  Per panel
+//   (1) ONE warp eliminates [A_pp | I] in registers, one row per lane (lanes 0..15: the A part, which becomes L_pp;
+//       lanes 16..31: the identity part, which becomes T_pp = L_pp^-1); pivots, columns of L and rows of T travel by
+//       warp shuffles -- a warp-shuffle panel factorisation with no block barrier inside its 16 dependent steps;
+//   (2) all threads: rows below  L_rp = A_rp T_pp^T  (triangular solve as a product with the sub-block's inverse);
+//   (3) rank-16 update of the trailing sub-matrix by DMMA on 8 x 8 fragments of its lower triangle.
+// Then T = L^-1 block by block, T_ij = -T_ii sum_{m=j..i-1} L_im T_mj for block distance 1, 2, 3, also by DMMA.
+// An earlier version swept the whole 64 x 64 block column by column with one __syncthreads per column (64 barriers,
+// everything in registers): 85 k cycles per block at B = 1 against 52 k for this one (instrumented build).
+// sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T (zeros above the
+// diagonal); dval[j] = L_jj; *s_bad = first non-positive pivot (1-based, global index).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void diag_chol_inv(double* sA, double* sT, double* vec /*[2][2][64]*/, double* dval /*[64]*/,
-                                              int* s_bad, int pivot_base) {
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double a[2][4][4];
+#ifdef AVN_FACTOR_PROF
+#define DPROF(slot)                                                                                  \
+  do {                                                                                               \
+    if (threadIdx.x == 0 && dprof) {                                                                 \
+      const long long dp_t1 = clock64();                                                             \
+      atomicAdd(reinterpret_cast<unsigned long long*>(dprof) + (slot), (unsigned long long)(dp_t1 - dp_t0)); \
+      dp_t0 = dp_t1;                                                                                 \
+    }                                                                                                \
+  } while (0)
+#else
+#define DPROF(slot)
+#endif
+__device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, double* dval /*[64]*/, int* s_bad,
+                                                      int pivot_base, long long* dprof = nullptr) {
+  constexpr int PB = 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, t = lane & 3;
+#ifdef AVN_FACTOR_PROF
+  long long dp_t0 = clock64();
+#endif
+  for (int p = 0; p < TILE / PB; p++) {
+    const int c0 = PB * p, c1 = c0 + PB;
+    if (warp == 0) {
+      // (1) elimination on [A_pp | I], one row per lane: lanes 0..15 hold the rows of the A part (they become L_pp
+      // column by column), lanes 16..31 the rows of the identity part (they become T_pp = L_pp^-1, row j final after
+      // step j).  Pivot, column j of L and row j of T travel by shuffles; no barrier, nothing in shared memory.
+      const int i = lane & 15;
+      const bool isA = lane < PB;
+      double x[PB];
 #pragma unroll
-  for (int h = 0; h < 2; h++)
+      for (int c = 0; c < PB; c++) x[c] = isA ? sA[(c0 + i) * FAC_LDS + c0 + c] : ((c == i) ? 1.0 : 0.0);
+      double pv = x[0];   // lane j: A_jj after the updates of steps < j, formed one step ahead (see below)
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const double2 v0 = *reinterpret_cast<const double2*>(&sA[(4 * (ty + 8 * h) + r) * FAC_LDS + 4 * tx]);
-      const double2 v1 = *reinterpret_cast<const double2*>(&sA[(4 * (ty + 8 * h) + r) * FAC_LDS + 4 * tx + 2]);
-      a[h][r][0] = v0.x; a[h][r][1] = v0.y; a[h][r][2] = v1.x; a[h][r][3] = v1.y;
-    }
-  __syncthreads();   // everyone holds its part of A: sA may now receive L
-  // zeros above the diagonal of L; column 0 of A for step 0
+      for (int j = 0; j < PB; j++) {
+        double piv = __shfl_sync(0xffffffffu, pv, j);
+        if (!(piv > 0.0)) {  // also catches NaN
+          if (lane == 0 && *s_bad == 0) *s_bad = pivot_base + c0 + j + 1;
+          piv = 1.0;
+        }
+        const double inv = rsqrt(piv);
+        const double liA = (i == j) ? piv * inv : x[j] * inv;       // A lanes: column j of L (rows >= j)
+        // the next pivot needs only lane j+1's own square: formed before any shuffle of this step
+        pv = fma(-liA, liA, x[(j + 1) & (PB - 1)]);
+        const double li = __shfl_sync(0xffffffffu, liA, i);          // T lanes: l of their row
+        // every lane executes every update; a zero multiplier leaves the entries of the other half alone
+        const double mA = isA ? -li : 0.0, mT = (!isA && i > j) ? -li : 0.0;
+        const bool rowj = !isA && i == j;
 #pragma unroll
-  for (int h = 0; h < 2; h++)
+        for (int c = j + 1; c < PB; c++) {
+          const double lc = __shfl_sync(0xffffffffu, li, c);
+          x[c] = fma(mA, lc, x[c]);                                  // right of the diagonal: never used
+        }
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int row = 4 * (ty + 8 * h) + r, col = 4 * tx + c;
-        if (col > row) sA[row * FAC_LDS + col] = 0.0;
+        for (int c = 0; c <= j; c++) {
+          const double trc = __shfl_sync(0xffffffffu, x[c], PB + j) * inv;   // final row j of T_pp
+          const double nv = fma(mT, trc, x[c]);
+          x[c] = rowj ? trc : nv;
+        }
+        x[j] = isA ? li : x[j];
       }
-  if (tx == 0) {
+      DPROF(8);
+      double* dst = isA ? sA : sT;
 #pragma unroll
-    for (int h = 0; h < 2; h++)
+      for (int c = 0; c < PB; c++) dst[(c0 + i) * FAC_LDS + c0 + c] = (c <= i) ? x[c] : 0.0;
+      if (isA) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) vec[4 * (ty + 8 * h) + r] = a[h][r][0];
-  }
-  for (int jb = 0; jb < 16; jb++) {
+        for (int c = 0; c < PB; c++)
+          if (c == i) dval[c0 + i] = x[c];
+      }
+    }
+    DPROF(9);
+    __syncthreads();
+    if (c1 < TILE) {
+      // (2) rows below the sub-block: L_rp = A_rp T_pp^T.  Thread = one column c of the panel and every 8th row; the
+      // row of T_pp sits in registers, T_pp[c][m] = 0 for m > c takes care of the triangle.
+      {
+        const int c = tid & 15, rbase = c1 + (tid >> 4);
+        double trow[PB], out[6];
 #pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      const int j = 4 * jb + jj;
-      const double* cur = vec + (j & 1) * 2 * TILE;        // [0..63] column j of A, [64..127] row j of the T part
-      double* nxt = vec + ((j + 1) & 1) * 2 * TILE;
+        for (int m = 0; m < PB; m++) trow[m] = sT[(c0 + c) * FAC_LDS + c0 + m];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          const int r = rbase + 8 * k;
+          const int rr = r < TILE ? r : TILE - 1;    // clamped: the value is not stored
+          double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+          for (int m = 0; m < PB; m += 2) {
+            acc0 = fma(sA[rr * FAC_LDS + c0 + m], trow[m], acc0);
+            acc1 = fma(sA[rr * FAC_LDS + c0 + m + 1], trow[m + 1], acc1);
+          }
+          out[k] = acc0 + acc1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          const int r = rbase + 8 * k;
+          if (r < TILE) sA[r * FAC_LDS + c0 + c] = out[k];
+        }
+      }
       __syncthreads();
-      double piv = cur[j];
-      if (!(piv > 0.0)) {  // also catches NaN
-        if (tid == 0 && *s_bad == 0) *s_bad = pivot_base + j + 1;
-        piv = 1.0;
+      DPROF(10);
+      // (3) trailing update A_rc -= sum_m L_r,c0+m L_c,c0+m for r >= c >= c1 on the tensor pipe: 8 x 8 fragments
+      // (fi, fj) of the lower triangle, dealt round-robin to the warps; conflict-free fragment loads (FAC_LDS)
+      {
+        const int f0 = c1 / 8, nf = TILE / 8 - f0;          // fragments per side of the trailing block
+        const int npairs = nf * (nf + 1) / 2;
+        for (int q = warp; q < npairs; q += FAC_THREADS / 32) {
+          int fi = 0;
+          while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
+          const int fj = q - fi * (fi + 1) / 2;
+          const int r0 = 8 * (f0 + fi), q0 = 8 * (f0 + fj);
+          double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < PB; kk += 4)
+            dmma884(acc0, acc1, sA[(r0 + gq) * FAC_LDS + c0 + kk + t], sA[(q0 + gq) * FAC_LDS + c0 + kk + t]);
+          double2* dst = reinterpret_cast<double2*>(&sA[(r0 + gq) * FAC_LDS + q0 + 2 * t]);
+          double2 cur = *dst;
+          cur.x -= acc0;
+          cur.y -= acc1;
+          *dst = cur;
+        }
       }
-      const double inv = rsqrt(piv);
-      if (tid == 0) dval[j] = piv * inv;
-      const int jn = (jj + 1) & 3;                // position of column / row j+1 inside its sub-block
-      const int jnb = (jj == 3) ? jb + 1 : jb;    // sub-block index of column / row j+1
+      __syncthreads();
+      DPROF(11);
+    }
+  }
+  // zeros above the diagonal outside the diagonal sub-blocks (L and T)
+  for (int e = tid; e < TILE * TILE; e += FAC_THREADS) {
+    const int r = e >> 6, c = e & 63;
+    if ((c >> 4) > (r >> 4)) {
+      sA[r * FAC_LDS + c] = 0.0;
+      sT[r * FAC_LDS + c] = 0.0;
+    }
+  }
+  // T off the diagonal, by block distance: W = sum_m L_im T_mj, then T_ij = -T_ii W, both on the tensor pipe.
+  // A 16 x 16 block is four 8 x 8 fragments; the (4 - dist) blocks of one distance give 4 (4 - dist) fragments,
+  // dealt round-robin to the warps (at most 3 per warp).
+  for (int dist = 1; dist < TILE / PB; dist++) {
+    const int nfr = 4 * (TILE / PB - dist);
+    __syncthreads();
+    double w0[3], w1[3];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int vty = ty + 8 * h;
-        if (vty < jb || tx > vty) continue;   // rows above the pivot block / sub-blocks above the diagonal
-        double lr[4];
-        {
-          const double2 p0 = *reinterpret_cast<const double2*>(&cur[4 * vty]);
-          const double2 p1 = *reinterpret_cast<const double2*>(&cur[4 * vty + 2]);
-          lr[0] = p0.x * inv; lr[1] = p0.y * inv; lr[2] = p1.x * inv; lr[3] = p1.y * inv;
-        }
-        if (tx > jb) {
-          // all four columns are right of j and all four rows below it: plain rank-1 update of A
-          const double2 q0 = *reinterpret_cast<const double2*>(&cur[4 * tx]);
-          const double2 q1 = *reinterpret_cast<const double2*>(&cur[4 * tx + 2]);
-          const double lc[4] = {q0.x * inv, q0.y * inv, q1.x * inv, q1.y * inv};
+    for (int u = 0; u < 3; u++) {
+      const int f = warp + 4 * u;
+      w0[u] = w1[u] = 0.0;
+      if (f < nfr) {
+        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
+        for (int m = bj * PB; m < bi * PB; m += 4)
+          dmma884(w0[u], w1[u], sA[(r0 + gq) * FAC_LDS + m + t], sT[(m + t) * FAC_LDS + q0 + gq]);
+      }
+    }
+    __syncthreads();
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+    for (int u = 0; u < 3; u++) {
+      const int f = warp + 4 * u;
+      if (f < nfr) {
+        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
+        *reinterpret_cast<double2*>(&sT[(r0 + gq) * FAC_LDS + q0 + 2 * t]) = make_double2(w0[u], w1[u]);
+      }
+    }
+    __syncthreads();
 #pragma unroll
-            for (int c = 0; c < 4; c++) a[h][r][c] = fma(-lr[r], lc[c], a[h][r][c]);
-        } else if (tx < jb) {
-          // all four columns are left of j: T part
-          const double2 q0 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx]);
-          const double2 q1 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx + 2]);
-          const double tr[4] = {q0.x * inv, q0.y * inv, q1.x * inv, q1.y * inv};   // final row j of T
+    for (int u = 0; u < 3; u++) {
+      const int f = warp + 4 * u;
+      w0[u] = w1[u] = 0.0;
+      if (f < nfr) {
+        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
 #pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const int row = 4 * vty + r;
-            if (row > j) {
+        for (int m = 0; m < PB; m += 4)
+          dmma884(w0[u], w1[u], sT[(r0 + gq) * FAC_LDS + bi * PB + m + t], sT[(bi * PB + m + t) * FAC_LDS + q0 + gq]);
+      }
+    }
+    __syncthreads();
 #pragma unroll
-              for (int c = 0; c < 4; c++) a[h][r][c] = fma(-lr[r], tr[c], a[h][r][c]);
-            } else if (row == j) {
-#pragma unroll
-              for (int c = 0; c < 4; c++) a[h][r][c] = tr[c];
-            }
-          }
-        } else {
-          // tx == jb: columns left of jj belong to the T part, column jj is turned from A into T, the rest is A
-          const double2 q0 = *reinterpret_cast<const double2*>(&cur[4 * tx]);
-          const double2 q1 = *reinterpret_cast<const double2*>(&cur[4 * tx + 2]);
-          const double2 t0 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx]);
-          const double2 t1 = *reinterpret_cast<const double2*>(&cur[TILE + 4 * tx + 2]);
-          const double lc[4] = {q0.x * inv, q0.y * inv, q1.x * inv, q1.y * inv};
-          const double tr[4] = {t0.x * inv, t0.y * inv, t1.x * inv, t1.y * inv};
-#pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const int row = 4 * vty + r;
-            if (row > j) {
-#pragma unroll
-              for (int c = 0; c < 4; c++) {
-                if (c < jj) a[h][r][c] = fma(-lr[r], tr[c], a[h][r][c]);
-                else if (c == jj) a[h][r][c] = -lr[r] * inv;
-                else a[h][r][c] = fma(-lr[r], lc[c], a[h][r][c]);
-              }
-              sA[row * FAC_LDS + j] = lr[r];
-            } else if (row == j) {
-#pragma unroll
-              for (int c = 0; c < 4; c++) {
-                if (c < jj) a[h][r][c] = tr[c];
-                else if (c == jj) a[h][r][c] = inv;
-              }
-              sA[row * FAC_LDS + j] = piv * inv;
-            }
-          }
-        }
-        // publish column j+1 of A and row j+1 of the T part (columns <= j) for the next step
-        if (j + 1 < TILE) {
-          if (tx == jnb) {
-#pragma unroll
-            for (int r = 0; r < 4; r++) nxt[4 * vty + r] = a[h][r][jn];
-          }
-          if (vty == jnb && tx <= jb) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) nxt[TILE + 4 * tx + c] = a[h][jn][c];
-          }
-        }
+    for (int u = 0; u < 3; u++) {
+      const int f = warp + 4 * u;
+      if (f < nfr) {
+        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
+        *reinterpret_cast<double2*>(&sT[(r0 + gq) * FAC_LDS + q0 + 2 * t]) = make_double2(-w0[u], -w1[u]);
       }
     }
   }
-#pragma unroll
-  for (int h = 0; h < 2; h++)
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int row = 4 * (ty + 8 * h) + r, col = 4 * tx + c;
-        sT[row * FAC_LDS + col] = (col <= row) ? a[h][r][c] : 0.0;
-      }
   __syncthreads();
+  DPROF(12);
 }
 
 __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
@@ -351,7 +402,6 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
   __shared__ int s_ticket;
   __shared__ int s_known;
   __shared__ int s_bad;
-  __shared__ __align__(16) double s_vec[4 * TILE];
   __shared__ double s_dval[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % 2, wn = warp / 2, gq = lane >> 2, t = lane & 3;
@@ -419,7 +469,9 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
         }
       if (tid == 0) s_bad = __ldcg(fa.info + b);
       __syncthreads();
-      diag_chol_inv(sA, sB, s_vec, s_dval, &s_bad, k0);
+      FPROF(7);
+      diag_chol_inv_blocked(sA, sB, s_dval, &s_bad, k0, fa.prof);
+      FPROF(6);
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
         *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sA[r * FAC_LDS + c]);
