@@ -173,6 +173,15 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use all the host's cores."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count(), user_api='blas')
+    except Exception:
+        pass
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -207,6 +216,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import gp_oracle as go
+    use_all_host_threads()
     _, X, y, th = workload_c2()
     spec = oracle_spec('c2')
     thetas = theta_cloud(th, max(args.steps + args.warmup, 4), seed=202)
@@ -458,6 +468,7 @@ def main():
             # which refactorises and recompiles on every call), 2 blocks of 4096 points, vectorised GH epilogue;
             # plus the reference's literal per-point GH loop (gpmcmc.py:549-563) on 10^4 points
             from oracle import gp_oracle as go
+            use_all_host_threads()
             spec4 = oracle_spec('c4')
             cores, api = blas_threads()
             t0 = time.perf_counter()
@@ -547,6 +558,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import gp_oracle as go
+        use_all_host_threads()
         spec = oracle_spec('c2')
         r0 = go.loglik(spec, th, X, y, want_grad=False, keep=True)
         sv = np.linalg.svd(r0.L, compute_uv=False)
