@@ -183,6 +183,23 @@ def gp_inputs(case):
     return X, y, th, Xs
 
 
+def next_row_outputs(spec, th, Xc, z, Xs):
+    """golden values of the "next" rows: the BO refine graph (latent mean / variance without the noise term
+    and their gradients w.r.t. the query points, gpmcmc.py:738-778) at the first 8 test points, and the inverse-problem
+    potential (gpmcmc.py:1098-1165, dense stacked system) at the first 4 for one observation with and without a
+    variance.  ``inv_noise_t`` is what the reference puts on the training diagonal: sqrt(gv + jitter)."""
+    from oracle import gp_oracle as go
+    pm, pv, pdm, pdv = go.predict_grad(spec, th, Xc, z, Xs[:8], pred_noise=False)
+    gv = go.unpack(spec, th)['gv']
+    noise_t = np.sqrt(gv + spec.jitter)
+    yo = np.array([0.3])
+    out = dict(pg_mu=pm, pg_var=pv, pg_dmu=pdm, pg_dvar=pdv, inv_yo=yo, inv_noise_t=np.array(noise_t))
+    for tag, noise_o in (('inv_ll_exact', 0.0), ('inv_ll_noisy', 0.05)):
+        ynoise = np.r_[np.full(len(z), noise_t), noise_o]
+        out[tag] = np.array([go.inverse_loglik(spec, th, Xc, z, x, yo, ynoise) for x in Xs[:4]])
+    return out
+
+
 def make_gp():
     from oracle import gp_oracle as go
     for name, case in gp_cases().items():
@@ -193,6 +210,7 @@ def make_gp():
         if case['M']:
             mu, var = go.predict(spec, th, r.Xw, r.z, Xs)
             out.update(Xs=Xs, mu=mu, var=var)
+            out.update(next_row_outputs(spec, th, r.Xw, r.z, Xs))
         np.savez(os.path.join(HERE, f'gp_oracle_{name}.npz'), **out)
         print(name, 'll', r.ll, 'P', len(th))
 

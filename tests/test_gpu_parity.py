@@ -101,6 +101,43 @@ def test_golden_predict(name):
     assert np.max(np.abs(var - g['var']) / np.maximum(np.abs(g['var']), kv)) <= 1e-8
 
 
+@pytest.mark.parametrize('name', ['m52_noise', 'm32_exp_sum', 'rbf_rq_prod'])
+def test_golden_next_rows(name):
+    """committed golden vectors of the "next" rows: predict_grad (BO refine graph, no noise term) and the
+    inverse-problem potential (block form on the device path against the oracle's dense stacked system)."""
+    from andvaranaut_b200.gp import GPEngine
+    from andvaranaut_b200.xpost import InverseLikelihood, kdiag_values
+    case = mg.gp_cases()[name]
+    g = np.load(os.path.join(HERE, 'golden', f'gp_oracle_{name}.npz'))
+    spec = case['spec']
+    th = g['theta']
+    hyp = go.unpack(spec, th)
+    eng = engine(spec)
+    eng.set_data(g['X'], g['y'])
+    assert int(eng.factorize(th)[0]) == 0
+    m, v, dm, dv = (t.cpu().numpy() for t in eng.predict_grad(g['Xs'][:8], pred_noise=False))
+    kv = go.kdiag_total(spec, hyp['kv'])
+    assert np.max(np.abs(m - g['pg_mu'])) <= 1e-8 * np.max(np.abs(g['pg_mu']))
+    assert np.max(np.abs(v - g['pg_var'])) <= 1e-8 * max(np.max(np.abs(g['pg_var'])), kv)
+    assert np.max(np.abs(dm - g['pg_dmu'])) <= 1e-8 * np.max(np.abs(g['pg_dmu']))
+    tol = 1e-6 if 'Exponential' in spec.kerns else 1e-8
+    assert np.max(np.abs(dv - g['pg_dvar'])) <= tol * max(np.max(np.abs(g['pg_dvar'])), kv)
+    # inverse problem: engine with the reference's diagonal (sqrt(gv + jitter), no jitter), constant = training ll
+    args = cases.engine_args(spec)
+    args.update(noise=True, jitter=0.0)
+    inv = GPEngine(**args)
+    inv.set_data(g['X'], g['y'])
+    thi = th.copy()
+    thi[0] = float(g['inv_noise_t'])
+    const = float(inv.loglik_grad(thi[None, :], want_grad=False)[0][0])
+    assert int(inv.factorize(thi)[0]) == 0
+    cfull, cdiag = kdiag_values(spec.kerns, spec.ops, hyp['kv'], hyp['alpha'])
+    for tag, noise_o in (('inv_ll_exact', 0.0), ('inv_ll_noisy', 0.05)):
+        pot = InverseLikelihood(inv, lambda x: (x, np.ones_like(x)), g['inv_yo'], noise_o, cfull - cdiag, const)
+        val, _ = pot(g['Xs'][:4])
+        assert np.max(np.abs(val - g[tag])) <= 1e-9 * np.max(np.abs(g[tag])), (tag, val, g[tag])
+
+
 SPECS = {
     'rbf_d2': (go.ModelSpec(nx=2, kerns=['RBF']), 64),            # exactly one tile
     'm52_d8': (go.ModelSpec(nx=8, kerns=['Matern52']), 65),       # one row into the second tile

@@ -148,6 +148,9 @@ def test_oracle_golden_fixtures_do_not_drift():
         if case['M']:
             mu, var = go.predict(case['spec'], th, r.Xw, r.z, Xs)
             assert np.allclose(mu, g['mu'], rtol=1e-8, atol=1e-9) and np.allclose(var, g['var'], rtol=1e-7, atol=1e-9)
+            nr = mg.next_row_outputs(case['spec'], th, r.Xw, r.z, Xs)
+            for k, v in nr.items():
+                assert np.allclose(v, g[k], rtol=1e-7, atol=1e-9 * max(1.0, float(np.max(np.abs(g[k]))))), (name, k)
 
 
 def test_tutorial_plausibility_band():
