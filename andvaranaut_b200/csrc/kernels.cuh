@@ -554,23 +554,33 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
     if (kd.noise) gr[kd.off_gv] = 0.5 * slots[nk * d + nk];
     if (kd.has_alpha) gr[kd.off_alpha] = 0.5 * slots[nk * d + nk + 1];
   }
-  // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p.  One warp per (dimension, parameter)
-  // pair: lanes stride over n, one shuffle reduction, no block-level barrier.
+  // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p.  One warp per (dimension, parameter) pair -- all pairs
+  // dealt to the 8 warps at once -- lanes stride over n (four rows in flight), one shuffle reduction, no barrier.
   if (kd.n_iw > 0) {
     const int nb = npad / TILE;
     // G[n][m] = sum over source tiles, already reduced into slab 0 by gx_reduce_kernel
     const double* G = ws.gxpart + (int64_t)b * nb * npad * d;
-    int poff = 0;
-    for (int m = 0; m < d; m++) {
-      const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;
-      for (int q = warp; q < np; q += 8) {
-        double acc = 0.0;
-        for (int n = lane; n < N; n += 32)
-          acc += G[(int64_t)n * d + m] * ws.dxw[(((int64_t)b * npad + n) * d + m) * MAXWP + q];
-        acc = warp_sum(acc);
-        if (lane == 0) gr[kd.off_iw + poff + q] = acc;
+    for (int pq = warp; pq < kd.n_iw; pq += 8) {
+      // pair index -> (dimension m, parameter q of its warp)
+      int m = 0, q = pq;
+      for (;; m++) {
+        const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;
+        if (q < np) break;
+        q -= np;
       }
-      poff += np;
+      const double* Gm = G + m;
+      const double* Dm = ws.dxw + (((int64_t)b * npad) * d + m) * MAXWP + q;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int n = lane;
+      for (; n + 96 < N; n += 128) {
+        a0 = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a0);
+        a1 = fma(Gm[(int64_t)(n + 32) * d], Dm[(int64_t)(n + 32) * d * MAXWP], a1);
+        a2 = fma(Gm[(int64_t)(n + 64) * d], Dm[(int64_t)(n + 64) * d * MAXWP], a2);
+        a3 = fma(Gm[(int64_t)(n + 96) * d], Dm[(int64_t)(n + 96) * d * MAXWP], a3);
+      }
+      for (; n < N; n += 32) a0 = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a0);
+      const double acc = warp_sum((a0 + a1) + (a2 + a3));
+      if (lane == 0) gr[kd.off_iw + pq] = acc;
     }
   }
   // learnable output warp: -alpha^T dz/dp + sum d log g'/dp
