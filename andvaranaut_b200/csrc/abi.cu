@@ -343,9 +343,9 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
     const double ntask_pr = (double)B * nb * (nb - 1) / 2 * (want_inverse ? 2 : 1);
     fprintf(stderr, "[factor prof] per task: diag %.0f cycles (x %d D tasks per sample), P/R epilogue %.0f cycles, P/R gemm %.0f cycles\n",
             (double)h[5] / ((double)B * nb), nb, (double)h[4] / ntask_pr, (double)h[2] / ntask_pr);
-    fprintf(stderr, "[factor prof] diag fn (thread 0 cycles per D task): warp elimination %.0f, store %.0f, trsm %.0f, syrk %.0f, T off-diagonal %.0f\n",
+    fprintf(stderr, "[factor prof] diag fn (thread 0 cycles per D task): warp cholesky %.0f, store %.0f, trsm %.0f, syrk %.0f, sub-block inverses %.0f, T off-diagonal %.0f\n",
             (double)h[8] / ((double)B * nb), (double)h[9] / ((double)B * nb), (double)h[10] / ((double)B * nb),
-            (double)h[11] / ((double)B * nb), (double)h[12] / ((double)B * nb));
+            (double)h[11] / ((double)B * nb), (double)h[13] / ((double)B * nb), (double)h[12] / ((double)B * nb));
     fprintf(stderr, "[factor prof] D task: stage %.0f cycles, chol+inverse %.0f cycles, store+publish %.0f cycles\n",
             (double)h[7] / ((double)B * nb), (double)h[6] / ((double)B * nb), (double)h[5] / ((double)B * nb));
   }

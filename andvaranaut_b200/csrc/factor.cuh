@@ -199,32 +199,25 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64 x 64 diagonal block: Cholesky AND triangular inverse, four 16-wide panels, 128 threads.  Per panel
-//   (1) ONE warp eliminates [A_pp | I] in registers, one row per lane (lanes 0..15: the A part, which becomes L_pp;
-//       lanes 16..31: the identity part, which becomes T_pp = L_pp^-1); pivots, columns of L and rows of T travel by
-//       warp shuffles -- a warp-shuffle panel factorisation with no block barrier inside its 16 dependent steps;
-//   (2) all threads: rows below  L_rp = A_rp T_pp^T  (triangular solve as a product with the sub-block's inverse);
+// 64 x 64 diagonal block: Cholesky, then the triangular inverse; 128 threads.
+// Cholesky in four 16-wide panels:
+//   (1) ONE warp factors the 16 x 16 diagonal sub-block in registers, one row per lane; pivot and column j of L travel
+//       by warp shuffles -- a warp-shuffle panel factorisation with no barrier inside its 16 dependent steps; the step
+//       is one basic block (branch-free pivot test and rsqrt), so the scheduler overlaps the rank-1 update of step j
+//       with the pivot chain (shuffle, rsqrt, scale) of step j + 1;
+//   (2) rows below:  x L_pp^T = a  by substitution, one row per thread in registers, L_pp broadcast from shared memory;
 //   (3) rank-16 update of the trailing sub-matrix by DMMA on 8 x 8 fragments of its lower triangle.
-// Then T = L^-1 block by block, T_ij = -T_ii sum_{m=j..i-1} L_im T_mj for block distance 1, 2, 3, also by DMMA.
-// An earlier version swept the whole 64 x 64 block column by column with one __syncthreads per column (64 barriers,
-// everything in registers): 85 k cycles per block at B = 1 against 52 k for this one (instrumented build).
+// Inverse: the four T_pp = L_pp^-1 in parallel (one warp each, one column per lane), then block by block
+// T_ij = -T_ii sum_{m=j..i-1} L_im T_mj for block distance 1, 2, 3 by DMMA.
+// History (instrumented build, cycles per diagonal task at B = 1, where these tasks ARE the critical path): a
+// register-resident column sweep of the whole block with one __syncthreads per column 85 k; panels with the inverse
+// fused into the warp elimination 52 k; Cholesky first + parallel sub-block inverses 36 k; branch-free steps 30.5 k.
 // sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T (zeros above the
-// diagonal); dval[j] = L_jj; *s_bad = first non-positive pivot (1-based, global index).
+// diagonal); dval[j] = L_jj; sinv[j] = 1 / L_jj; *s_bad = first non-positive pivot (1-based, global index).
 // ------------------------------------------------------------------------------------------------
-#ifdef AVN_FACTOR_PROF
-#define DPROF(slot)                                                                                  \
-  do {                                                                                               \
-    if (threadIdx.x == 0 && dprof) {                                                                 \
-      const long long dp_t1 = clock64();                                                             \
-      atomicAdd(reinterpret_cast<unsigned long long*>(dprof) + (slot), (unsigned long long)(dp_t1 - dp_t0)); \
-      dp_t0 = dp_t1;                                                                                 \
-    }                                                                                                \
-  } while (0)
-#else
-#define DPROF(slot)
-#endif
-__device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, double* dval /*[64]*/, int* s_bad,
-                                                      int pivot_base, long long* dprof = nullptr) {
+__device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, double* dval /*[64]*/,
+                                                      double* sinv /*[64]*/, int* s_bad, int pivot_base,
+                                                      long long* dprof = nullptr) {
   constexpr int PB = 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -234,80 +227,65 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
   for (int p = 0; p < TILE / PB; p++) {
     const int c0 = PB * p, c1 = c0 + PB;
     if (warp == 0) {
-      // (1) elimination on [A_pp | I], one row per lane: lanes 0..15 hold the rows of the A part (they become L_pp
-      // column by column), lanes 16..31 the rows of the identity part (they become T_pp = L_pp^-1, row j final after
-      // step j).  Pivot, column j of L and row j of T travel by shuffles; no barrier, nothing in shared memory.
+      // (1) Cholesky of the 16 x 16 diagonal sub-block, one row per lane in registers (lanes 16..31 shadow lanes
+      // 0..15 so that every shuffle is a full-warp one).  Pivot and column j of L travel by shuffles: no barrier,
+      // nothing in shared memory inside the 16 dependent steps.
       const int i = lane & 15;
-      const bool isA = lane < PB;
       double x[PB];
 #pragma unroll
-      for (int c = 0; c < PB; c++) x[c] = isA ? sA[(c0 + i) * FAC_LDS + c0 + c] : ((c == i) ? 1.0 : 0.0);
+      for (int c = 0; c < PB; c++) x[c] = sA[(c0 + i) * FAC_LDS + c0 + c];
       double pv = x[0];   // lane j: A_jj after the updates of steps < j, formed one step ahead (see below)
+      double myinv = 1.0;
+      int badj = 0;       // first non-positive pivot of this sub-block (1-based), 0: none
 #pragma unroll
       for (int j = 0; j < PB; j++) {
         double piv = __shfl_sync(0xffffffffu, pv, j);
-        if (!(piv > 0.0)) {  // also catches NaN
-          if (lane == 0 && *s_bad == 0) *s_bad = pivot_base + c0 + j + 1;
-          piv = 1.0;
-        }
-        const double inv = rsqrt(piv);
-        const double liA = (i == j) ? piv * inv : x[j] * inv;       // A lanes: column j of L (rows >= j)
+        const bool bad = !(piv > 0.0);   // also catches NaN
+        badj = (bad && badj == 0) ? j + 1 : badj;
+        piv = bad ? 1.0 : piv;
+        const double inv = rsqrt_nobranch(piv);
+        myinv = (i == j) ? inv : myinv;
+        const double li = (i == j) ? piv * inv : x[j] * inv;        // column j of L (rows >= j)
         // the next pivot needs only lane j+1's own square: formed before any shuffle of this step
-        pv = fma(-liA, liA, x[(j + 1) & (PB - 1)]);
-        const double li = __shfl_sync(0xffffffffu, liA, i);          // T lanes: l of their row
-        // every lane executes every update; a zero multiplier leaves the entries of the other half alone
-        const double mA = isA ? -li : 0.0, mT = (!isA && i > j) ? -li : 0.0;
-        const bool rowj = !isA && i == j;
+        pv = fma(-li, li, x[(j + 1) & (PB - 1)]);
 #pragma unroll
         for (int c = j + 1; c < PB; c++) {
           const double lc = __shfl_sync(0xffffffffu, li, c);
-          x[c] = fma(mA, lc, x[c]);                                  // right of the diagonal: never used
+          x[c] = fma(-li, lc, x[c]);                                 // right of the diagonal: never used
         }
-#pragma unroll
-        for (int c = 0; c <= j; c++) {
-          const double trc = __shfl_sync(0xffffffffu, x[c], PB + j) * inv;   // final row j of T_pp
-          const double nv = fma(mT, trc, x[c]);
-          x[c] = rowj ? trc : nv;
-        }
-        x[j] = isA ? li : x[j];
+        x[j] = li;
       }
       DPROF(8);
-      double* dst = isA ? sA : sT;
+      if (lane == 0 && badj != 0 && *s_bad == 0) *s_bad = pivot_base + c0 + badj;
+      if (lane < PB) {
 #pragma unroll
-      for (int c = 0; c < PB; c++) dst[(c0 + i) * FAC_LDS + c0 + c] = (c <= i) ? x[c] : 0.0;
-      if (isA) {
-#pragma unroll
-        for (int c = 0; c < PB; c++)
+        for (int c = 0; c < PB; c++) {
+          sA[(c0 + i) * FAC_LDS + c0 + c] = (c <= i) ? x[c] : 0.0;
           if (c == i) dval[c0 + i] = x[c];
+        }
+        sinv[c0 + i] = myinv;       // 1 / L_ii (rsqrt of the pivot, as T_ii is defined)
       }
     }
     DPROF(9);
     __syncthreads();
     if (c1 < TILE) {
-      // (2) rows below the sub-block: L_rp = A_rp T_pp^T.  Thread = one column c of the panel and every 8th row; the
-      // row of T_pp sits in registers, T_pp[c][m] = 0 for m > c takes care of the triangle.
+      // (2) rows below the sub-block: x L_pp^T = a by substitution, one row per thread in registers; L_pp is read from
+      // shared memory (every thread the same address: broadcast).  As soon as x_m is known every later column is updated
+      // (independent FMAs), so the dependent depth is 16 x (multiply + FMA).
       {
-        const int c = tid & 15, rbase = c1 + (tid >> 4);
-        double trow[PB], out[6];
+        const int r = c1 + tid;
+        if (r < TILE) {
+          double a[PB];
 #pragma unroll
-        for (int m = 0; m < PB; m++) trow[m] = sT[(c0 + c) * FAC_LDS + c0 + m];
+          for (int m = 0; m < PB; m++) a[m] = sA[r * FAC_LDS + c0 + m];
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-          const int r = rbase + 8 * k;
-          const int rr = r < TILE ? r : TILE - 1;    // clamped: the value is not stored
-          double acc0 = 0.0, acc1 = 0.0;
+          for (int m = 0; m < PB; m++) {
+            a[m] *= sinv[c0 + m];
 #pragma unroll
-          for (int m = 0; m < PB; m += 2) {
-            acc0 = fma(sA[rr * FAC_LDS + c0 + m], trow[m], acc0);
-            acc1 = fma(sA[rr * FAC_LDS + c0 + m + 1], trow[m + 1], acc1);
+            for (int c = m + 1; c < PB; c++) a[c] = fma(-a[m], sA[(c0 + c) * FAC_LDS + c0 + m], a[c]);
           }
-          out[k] = acc0 + acc1;
-        }
-        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-          const int r = rbase + 8 * k;
-          if (r < TILE) sA[r * FAC_LDS + c0 + c] = out[k];
+          for (int m = 0; m < PB; m++) sA[r * FAC_LDS + c0 + m] = a[m];
         }
       }
       __syncthreads();
@@ -345,6 +323,29 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
       sT[r * FAC_LDS + c] = 0.0;
     }
   }
+  // inverses of the four diagonal sub-blocks, one per warp: lane c owns column c of T_pp (forward substitution down
+  // the column, two interleaved partial sums); T_cc = rsqrt(pivot)
+  {
+    const int c0 = PB * warp, c = lane & 15;
+    double tcol[PB];
+#pragma unroll
+    for (int r = 0; r < PB; r++) {
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < r; m++) {
+        const double tm = (m >= c) ? tcol[m] : 0.0;
+        if (m & 1) acc1 = fma(sA[(c0 + r) * FAC_LDS + c0 + m], tm, acc1);
+        else acc0 = fma(sA[(c0 + r) * FAC_LDS + c0 + m], tm, acc0);
+      }
+      const double ir = sinv[c0 + r];
+      tcol[r] = (r == c) ? ir : ((r > c) ? -(acc0 + acc1) * ir : 0.0);
+    }
+    if (lane < PB) {
+#pragma unroll
+      for (int r = 0; r < PB; r++) sT[(c0 + r) * FAC_LDS + c0 + c] = tcol[r];
+    }
+  }
+  DPROF(13);
   // T off the diagonal, by block distance: W = sum_m L_im T_mj, then T_ij = -T_ii W, both on the tensor pipe.
   // A 16 x 16 block is four 8 x 8 fragments; the (4 - dist) blocks of one distance give 4 (4 - dist) fragments,
   // dealt round-robin to the warps (at most 3 per warp).
@@ -403,6 +404,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
   __shared__ int s_known;
   __shared__ int s_bad;
   __shared__ double s_dval[TILE];
+  __shared__ double s_inv[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % 2, wn = warp / 2, gq = lane >> 2, t = lane & 3;
   const int npad = fa.npad, nb = fa.nb, B = fa.B;
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       if (tid == 0) s_bad = __ldcg(fa.info + b);
       __syncthreads();
       FPROF(7);
-      diag_chol_inv_blocked(sA, sB, s_dval, &s_bad, k0, fa.prof);
+      diag_chol_inv_blocked(sA, sB, s_dval, s_inv, &s_bad, k0, fa.prof);
       FPROF(6);
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
