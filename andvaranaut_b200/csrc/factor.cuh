@@ -215,6 +215,29 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 // sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T (zeros above the
 // diagonal); dval[j] = L_jj; sinv[j] = 1 / L_jj; *s_bad = first non-positive pivot (1-based, global index).
 // ------------------------------------------------------------------------------------------------
+// 1 / sqrt(p) for a normal positive p: the hardware estimate (MUFU.RSQ64H, ~2^-22) and one third-order correction
+// y (1 + e/2 + 3 e^2 / 8), e = 1 - p y^2 -- the fast path of the library rsqrt() without its range check and call, so
+// that a whole pivot step stays one basic block and the scheduler can overlap it with the updates of the previous one.
+__device__ __forceinline__ double rsqrt_nobranch(double p) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  const double e = fma(-(y * y), p, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(c, y * e, y);
+}
+
+#ifdef AVN_FACTOR_PROF
+#define DPROF(slot)                                                                                  \
+  do {                                                                                               \
+    if (threadIdx.x == 0 && dprof) {                                                                 \
+      const long long dp_t1 = clock64();                                                             \
+      atomicAdd(reinterpret_cast<unsigned long long*>(dprof) + (slot), (unsigned long long)(dp_t1 - dp_t0)); \
+      dp_t0 = dp_t1;                                                                                 \
+    }                                                                                                \
+  } while (0)
+#else
+#define DPROF(slot)
+#endif
 __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, double* dval /*[64]*/,
                                                       double* sinv /*[64]*/, int* s_bad, int pivot_base,
                                                       long long* dprof = nullptr) {
