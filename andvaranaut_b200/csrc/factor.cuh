@@ -497,20 +497,23 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       FPROF(7);
       diag_chol_inv_blocked(sA, sB, s_dval, s_inv, &s_bad, k0, fa.prof);
       FPROF(6);
+      // T_kk is what the panel and inverse tasks of this step wait for: stored and published first; L_kk itself is
+      // read by no task of this kernel and follows behind the flags
+      for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sB[r * FAC_LDS + c]);
+      }
+      if (tid == 0) fa.info[b] = s_bad;
+      publish2(lflag + k, k + 1, tflag + k, k + 1);
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
         *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sA[r * FAC_LDS + c]);
-        *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sB[r * FAC_LDS + c]);
       }
       if (warp == 0) {   // sum of log L_ii in a fixed order
         double v = log(s_dval[lane]) + log(s_dval[lane + 32]);
         v = warp_sum(v);
-        if (lane == 0) {
-          fa.fpart[((int64_t)b * nb + k) * 2 + 1] = v;
-          fa.info[b] = s_bad;
-        }
+        if (lane == 0) fa.fpart[((int64_t)b * nb + k) * 2 + 1] = v;
       }
-      publish2(lflag + k, k + 1, tflag + k, k + 1);
       FPROF(5);
     } else if (type == 1) {
       // ---------------- P(b,k,i) ----------------

@@ -34,6 +34,7 @@ def run(N, iters=3, d=12, seed=505):
     torch.cuda.synchronize()
     t_fit0 = time.perf_counter() - t0
     t_acq = t_fit = 0.0
+    evals = []
     y0 = g.y.min()
     for it in range(iters):
         t0 = time.perf_counter()
@@ -44,13 +45,14 @@ def run(N, iters=3, d=12, seed=505):
         t_acq += time.perf_counter() - t0
         t0 = time.perf_counter()
         g.set_data(np.r_[g.x, xn], np.r_[g.y, np.array([target(xn[0])])])
-        g.fit(method='map', start=g.hypers)
+        data = g.fit(method='map', start=g.hypers, return_data=True)
         torch.cuda.synchronize()
         t_fit += time.perf_counter() - t0
+        evals.append(int(data['evals']))
     return {'N': N, 'd': d, 'candidates': 4096, 'iters': iters, 'first_fit_s': round(t_fit0, 3),
             'acquire_ms': round(1e3 * t_acq / iters, 2), 'refit_ms': round(1e3 * t_fit / iters, 2),
             'iters_per_s': round(iters / (t_acq + t_fit), 3), 'best_y': float(g.y.min()), 'start_best_y': float(y0),
-            'evals_last_fit': None}
+            'refit_evals': evals}
 
 
 if __name__ == '__main__':
