@@ -461,3 +461,13 @@ def test_rank1_append_rejects_a_non_positive_pivot():
         assert np.array_equal(eng.predict(Xs)[0].cpu().numpy(), mu0)
     else:
         assert eng.N == 51
+
+
+def test_randomised_sweep():
+    """tools/fuzz_parity.py: random N (2 .. 300, around the 64-row slab boundaries), d, kernel folds, noise, batch and
+    test-batch sizes (1 .. 4097: every row-split regime of the predict kernels), three rank-1 appends each; every
+    quantity against the oracle at the tolerances of this module (scaled by cond(K) eps where that is larger)."""
+    import subprocess
+    tool = os.path.join(os.path.dirname(HERE), 'tools', 'fuzz_parity.py')
+    r = subprocess.run([sys.executable, tool, '40', '11'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
