@@ -36,6 +36,8 @@ class Posterior:
         theta, dxdz, ljac, dljac = self.space.theta_from_z(z)
         if self.shard is not None:
             ll, gll, info = self.shard.loglik_grad(self.engine, theta)
+        elif hasattr(self.engine, 'loglik_grad_host'):
+            ll, gll, info = self.engine.loglik_grad_host(theta)      # one packed device->host copy
         else:
             ll_t, g_t, info_t = self.engine.loglik_grad(theta)
             ll, gll, info = ll_t.cpu().numpy(), g_t.cpu().numpy(), info_t.cpu().numpy()

@@ -178,6 +178,26 @@ class GPEngine:
         self._last_B = B
         return ll, grad, info
 
+    def loglik_grad_host(self, theta):
+        """host arrays in, host arrays out: theta [B,P] NumPy -> (ll [B], grad [B,P], info [B]) NumPy.  The three results
+        live in ONE device buffer and come back with one device->host copy (the optimiser / sampler drivers call this
+        once per step, where three separate synchronising copies cost ~0.1 ms of a 1.4 ms evaluation)."""
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        B, P = theta.shape
+        n = B * (P + 2)
+        if getattr(self, '_pack', None) is None or self._pack.numel() != n:
+            self._pack = torch.empty(n, dtype=torch.float64, device=self.device)
+            self._pack_host = torch.empty(n, dtype=torch.float64).pin_memory()
+            self._theta_host = torch.empty(B, P, dtype=torch.float64).pin_memory()
+        buf = self._pack
+        out = (buf[:B], buf[B:B + B * P].view(B, P), buf[B + B * P:].view(torch.int32)[:B])
+        self._theta_host.copy_(torch.from_numpy(theta))
+        self.loglik_grad(self._theta_host.to(self.device, non_blocking=True), out=out)
+        self._pack_host.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self._pack_host.numpy()
+        return h[:B].copy(), h[B:B + B * P].reshape(B, P).copy(), h[B + B * P:].view(np.int32)[:B].copy()
+
     def cov(self, theta):
         theta = self._dev(theta)
         if theta.ndim == 1:
