@@ -322,8 +322,9 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   fa.prof = nullptr;
 #ifdef AVN_FACTOR_PROF
   static long long* prof_dev = nullptr;
-  if (!prof_dev) cudaMalloc(&prof_dev, 128);
-  cudaMemsetAsync(prof_dev, 0, 128, st);
+  const size_t prof_bytes = (16 + 4 * 4000) * 8;
+  if (!prof_dev) cudaMalloc(&prof_dev, prof_bytes);
+  cudaMemsetAsync(prof_dev, 0, prof_bytes, st);
   fa.prof = prof_dev;
 #endif
   {
@@ -346,6 +347,22 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
     fprintf(stderr, "[factor prof] diag fn (thread 0 cycles per D task): warp cholesky %.0f, store %.0f, trsm %.0f, syrk %.0f, sub-block inverses %.0f, T off-diagonal %.0f\n",
             (double)h[8] / ((double)B * nb), (double)h[9] / ((double)B * nb), (double)h[10] / ((double)B * nb),
             (double)h[11] / ((double)B * nb), (double)h[13] / ((double)B * nb), (double)h[12] / ((double)B * nb));
+    if (B == 1 && getenv("AVN_FACTOR_TIMELINE")) {
+      static long long ev[4 * 4000];
+      long long cnt = h[15] < 4000 ? h[15] : 4000;
+      cudaMemcpy(ev, prof_dev + 16, sizeof(long long) * 4 * cnt, cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (long long q = 0; q < cnt; q++)
+        if (ev[4 * q] == 0 && ev[4 * q + 1] == 8 && ev[4 * q + 2] == 0) t0 = ev[4 * q + 3];
+      const char* names[2][7] = {{"D start", "D update done", "D chol+inv done", "D published", "D pipeline done", "D flag seen", "D tile staged"},
+                                 {"P start", "P gemm done", "P has T_kk", "P published", "", "", ""}};
+      for (int kq = 8; kq <= 10; kq++)
+        for (int ty = 0; ty < 2; ty++)
+          for (int evn = 0; evn < 7; evn++)
+            for (long long q = 0; q < cnt; q++)
+              if (ev[4 * q] == ty && ev[4 * q + 1] == kq && ev[4 * q + 2] == evn)
+                fprintf(stderr, "[timeline] k=%d %-18s %8.2f us\n", kq, names[ty][evn], (ev[4 * q + 3] - t0) * 1e-3);
+    }
     fprintf(stderr, "[factor prof] D task: stage %.0f cycles, chol+inverse %.0f cycles, store+publish %.0f cycles\n",
             (double)h[7] / ((double)B * nb), (double)h[6] / ((double)B * nb), (double)h[5] / ((double)B * nb));
   }

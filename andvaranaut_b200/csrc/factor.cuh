@@ -39,6 +39,19 @@ constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 constexpr size_t FAC_SMEM_BYTES = cmax((size_t)2 * TILE * FAC_LDS * 8, cmax(FacKK::SMEM_BYTES, FacKR::SMEM_BYTES));
 
 #ifdef AVN_FACTOR_PROF
+// timeline of the critical chain (B = 1): thread 0 logs (task type, k, event, globaltimer ns) for the diagonal tasks
+// and the panel tile right below the diagonal into prof[16 ...] (4 long long per entry, entry count in prof[15])
+__device__ __forceinline__ void fprof_event(long long* prof, int type, int k, int ev) {
+  if (threadIdx.x != 0 || !prof) return;
+  unsigned long long ns;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+  const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(prof) + 15, 1ull);
+  if (slot < 4000) {
+    long long* e = prof + 16 + 4 * slot;
+    e[0] = type; e[1] = k; e[2] = ev; e[3] = (long long)ns;
+  }
+}
+#define FEVENT(type, k, ev) fprof_event(fa.prof, type, k, ev)
 #define FPROF_DECL long long fp_t0 = clock64(), fp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define FPROF(slot)                                   \
   do {                                                \
@@ -52,6 +65,7 @@ constexpr size_t FAC_SMEM_BYTES = cmax((size_t)2 * TILE * FAC_LDS * 8, cmax(FacK
       for (int q = 0; q < 8; q++) atomicAdd(reinterpret_cast<unsigned long long*>(p) + q, (unsigned long long)fp_acc[q]); \
   } while (0)
 #else
+#define FEVENT(type, k, ev)
 #define FPROF_DECL
 #define FPROF(slot)
 #define FPROF_FLUSH(p)
@@ -191,10 +205,17 @@ __device__ __forceinline__ void smem_gemm64x(double (&acc)[4][4][2], const doubl
 // copy a 64 x 64 global tile (row stride ld) into a staged shared tile, bypassing L1 (the data was written by
 // another SM during this launch)
 __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__ g, int64_t ld) {
-  for (int e = threadIdx.x; e < TILE * TILE / 2; e += FAC_THREADS) {
-    const int r = e >> 5, c = (e & 31) * 2;
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(g + (int64_t)r * ld + c));
-    *reinterpret_cast<double2*>(&s[r * FAC_LDS + c]) = v;
+  constexpr int PER = TILE * TILE / 2 / FAC_THREADS;   // 16 double2 per thread: all loads issued before the first store
+  double2 v[PER];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int e = threadIdx.x + q * FAC_THREADS, r = e >> 5, c = (e & 31) * 2;
+    v[q] = __ldcg(reinterpret_cast<const double2*>(g + (int64_t)r * ld + c));
+  }
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int e = threadIdx.x + q * FAC_THREADS, r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(&s[r * FAC_LDS + c]) = v[q];
   }
 }
 
@@ -476,13 +497,29 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       // ---------------- D(b,k) ----------------
       double* Akk = L + (int64_t)k0 * npad + k0;
       double* Tkk = T + (int64_t)k0 * npad + k0;
+      FEVENT(0, k, 0);
       FacKK g;
       load_neg_tile(g.acc, Akk, npad, wm, wn, gq, t);
       if (k > 0) {
-        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
         // only the lower triangle of the block is used: the warp of the upper-right quadrant computes nothing
-        g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0, [&](int kt) { w(kt); },
-              (wm == 0 && wn == 1) ? 0x7fffffff : 0);
+        const bool idle_quadrant = (wm == 0 && wn == 1);
+        if (k > 1) {
+          // block columns 0 .. k-2 of row k through the pipeline: final long before this task is on the critical path
+          SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
+          g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0 - TILE,
+                [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
+        }
+        // block column k-1 is what the whole factorisation waits for (it is published by the panel task of the previous
+        // step): the 64 x 64 tile is fetched in ONE round of loads -- every thread has its sixteen 16-byte loads in flight
+        // at once -- instead of four pipeline slabs issued two at a time (two L2 round trips and four barriers)
+        FEVENT(0, k, 4);
+        wait_flag(lflag + k, k, fa.ctl);
+        FEVENT(0, k, 5);
+        stage_tile(sA, L + (int64_t)k0 * npad + (k0 - TILE), npad);
+        __syncthreads();
+        FEVENT(0, k, 6);
+        if (!idle_quadrant) smem_gemm64x<false>(g.acc, sA, sA, wm, wn, gq, t, TILE);
+        __syncthreads();   // sA is overwritten with the updated block below
         FPROF(2);
       }
 #pragma unroll
@@ -492,11 +529,13 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
           *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
         }
+      FEVENT(0, k, 1);
       if (tid == 0) s_bad = __ldcg(fa.info + b);
       __syncthreads();
       FPROF(7);
       diag_chol_inv_blocked(sA, sB, s_dval, s_inv, &s_bad, k0, fa.prof);
       FPROF(6);
+      FEVENT(0, k, 2);
       // T_kk is what the panel and inverse tasks of this step wait for: stored and published first; L_kk itself is
       // read by no task of this kernel and follows behind the flags
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
@@ -505,6 +544,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       }
       if (tid == 0) fa.info[b] = s_bad;
       publish2(lflag + k, k + 1, tflag + k, k + 1);
+      FEVENT(0, k, 3);
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
         *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sA[r * FAC_LDS + c]);
@@ -519,6 +559,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       // ---------------- P(b,k,i) ----------------
       const int i = idx, i0 = i * TILE;
       double* Aik = L + (int64_t)i0 * npad + k0;
+      if (i == k + 1) FEVENT(1, k, 0);
       FacKK g;
       load_neg_tile(g.acc, Aik, npad, wm, wn, gq, t);
       if (k > 0) {
@@ -535,8 +576,10 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
         }
       FPROF(4);
+      if (i == k + 1) FEVENT(1, k, 1);
       wait_flag(lflag + k, k + 1, fa.ctl);   // T[k,k] is there (also orders the sA writes)
       FPROF(3);
+      if (i == k + 1) FEVENT(1, k, 2);
       stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
       __syncthreads();
       g.zero();
@@ -549,6 +592,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           *reinterpret_cast<double2*>(Aik + (int64_t)r * npad + c) = make_double2(g.acc[ii][j][0], g.acc[ii][j][1]);
         }
       publish(lflag + i, k + 1);
+      if (i == k + 1) FEVENT(1, k, 3);
       FPROF(4);
     } else {
       // ---------------- R(b,k,j) ----------------
