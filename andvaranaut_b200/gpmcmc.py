@@ -71,6 +71,14 @@ class GPMCMC(LHC):
         self.xopt = self.yopt = None
         self.shard = None          # optional andvaranaut_b200.dist.Shard for multi-GPU runs
 
+    # ---- pickling (save_object / load_object, core.py): device state is dropped and rebuilt on the next predict ----
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st['gp'] = None
+        st['_pred_cache'] = None
+        st['shard'] = None
+        return st
+
     # ---- small pieces of state management --------------------------------------------------------
     def zero_mean(self, x):
         return np.zeros(self.ny)

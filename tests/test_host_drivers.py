@@ -317,3 +317,24 @@ def test_nuts_and_hmc_sample_a_known_density():
             n = tr.sample_stats['n_steps']
             assert n.min() >= 1 and n.max() <= 1023 and np.all(tr.sample_stats['tree_depth'] <= 10)
             assert len(np.unique(n)) > 1            # chains stop at different depths within one lock-step transition
+
+
+def test_gpmcmc_pickles_without_device_state(tmp_path):
+    """save_object / load_object (andvaranaut/core.py) on a surrogate: the engine handle, the cached factorisation and
+    the process-group shard are dropped; data, conversions and fitted hypers survive."""
+    from andvaranaut_b200 import GPMCMC, save_object, load_object, meanstd
+    g = GPMCMC(kernel='Matern52', noise=True, nx=2, ny=1, priors=[st.uniform(0, 1)] * 2, target=lambda x: np.array([x[0] + x[1]]),
+               verbose=False, rundir=str(tmp_path / 'runs'))
+    rng = np.random.default_rng(0)
+    x = rng.uniform(size=(12, 2))
+    g.set_data(x, (x[:, 0] + x[:, 1])[:, None])
+    g.change_yconrevs([meanstd(g.y[:, 0])])
+    g.hypers = {'gv': np.array(1e-4), 'l': np.array([1.0, 2.0]), 'kv': np.array([1.5])}
+    g.gp = object()                 # stands for a GPEngine (ctypes handle + device tensors: not picklable state)
+    g._pred_cache = ((1e-6, 12), g.gp, None)
+    f = str(tmp_path / 'g.pickle')
+    save_object(g, f)
+    h = load_object(f)
+    assert h.gp is None and h._pred_cache is None and h.shard is None
+    assert np.array_equal(h.x, g.x) and np.array_equal(h.yc, g.yc) and np.array_equal(h.hypers['l'], g.hypers['l'])
+    assert g.gp is not None       # the live object keeps its device state
