@@ -475,6 +475,33 @@ class GPMCMC(LHC):
             print(f"R^2 for y is: {out['r2']:0.5f}")
         return out
 
+    def y_dist(self, mode='hist_kde', nsamps=None, return_data=False, surrogate=True, seed=None):
+        """distribution of the output over the input priors (gpmcmc.py:140-151): ``nsamps`` LHC points through the
+        surrogate (one batched device predict) or the stored data; the seaborn plot of the reference is drawn only when
+        seaborn / matplotlib are installed (plotting is out of scope here), the data come back with ``return_data``."""
+        if mode not in ('hist', 'kde', 'ecdf', 'hist_kde'):
+            raise Exception("Error: selected mode must be one of ['hist', 'kde', 'ecdf', 'hist_kde']")
+        if not isinstance(surrogate, bool):
+            raise Exception('Error: surrogate argument must be of type bool')
+        if surrogate:
+            xs = self._LHC__latin_sample(nsamps, seed=seed)
+            ys = self.predict(xs)
+        else:
+            xs, ys = self.x, self.y
+        try:
+            import seaborn as sns
+            import matplotlib.pyplot as plt
+            kw = dict(hist=dict(kind='hist'), kde=dict(kind='kde'), ecdf=dict(kind='ecdf'), hist_kde=dict(kind='hist', kde=True))
+            for i in range(self.ny):
+                sns.displot(ys[:, i], **kw[mode])
+                plt.xlabel(f'y[{i}]')
+                plt.ylabel('Density')
+                plt.show()
+        except ImportError:
+            pass
+        if return_data and surrogate:
+            return xs, ys
+
     def relative_importances(self):
         ls = np.asarray(self.hypers['l']).reshape(self.nkern, self.nx)
         inv = 1.0 / ls

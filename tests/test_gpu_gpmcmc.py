@@ -292,3 +292,14 @@ def test_appended_points_extend_the_cached_factorisation(tmp_path):
     assert g._pred_cache[1] is not eng0
     assert np.max(np.abs(m1 - m2)) <= 1e-8 * np.max(np.abs(m2))
     assert np.max(np.abs(v1 - v2)) <= 1e-8 * np.max(np.abs(v2)) + 1e-12
+
+
+def test_y_dist_returns_surrogate_samples(tmp_path):
+    g = tutorial_gp(tmp_path, kernel='RBF', noise=True, n=40)
+    g.fit()
+    xs, ys = g.y_dist(nsamps=300, return_data=True, seed=3)
+    assert xs.shape == (300, 2) and ys.shape == (300, 1)
+    truth = np.array([target_fun(x)[0] for x in xs])
+    assert np.sqrt(np.mean((ys[:, 0] - truth) ** 2)) < 0.05
+    with pytest.raises(Exception, match='mode must be one of'):
+        g.y_dist(mode='violin', nsamps=10)
