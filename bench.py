@@ -546,9 +546,11 @@ def main():
                                        'still-growing chains is one batched avn_gp_loglik_grad call; host-timed end to end'}
             del eng3
             extra['next_rows'] = nrow
-        # c5: Bayesian-optimisation iterations through the GPMCMC API (rank 0 only: one sequential optimiser)
+        # c1 (the reference's own tutorial case) and c5 through the GPMCMC API (rank 0 only: sequential optimisers)
         if rank == 0:
             sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import c1_tutorial_probe
+            extra['c1_tutorial'] = c1_tutorial_probe.run()
             import c5_bo_probe
             extra['c5_bo'] = {'metric': 'bo_iterations_per_s', 'workload': 'd=12, 4096 LHC candidates -> EI -> argmax -> '
                               'append -> warm-started MAP refit, at three training-set sizes (3 iterations each)',
