@@ -315,7 +315,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   int rc = factor_grid(total, &grid);
   if (rc) return rc;
   FactorArgs fa;
-  fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info;
+  fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info; fa.z = W.z; fa.beta = W.beta;
   fa.lflag = W.lflag; fa.tflag = W.tflag; fa.ctl = W.ctl;
   fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.n = (int)gp->N; fa.want_inverse = want_inverse ? 1 : 0;
   fa.dgap = 0;   // D(.,s+1) right behind P(.,s,s+1): its first s slabs are final already, only the last one waits
@@ -375,8 +375,8 @@ static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, 
   const dim3 grid((unsigned)(npad / TILE), (unsigned)B);
   {
     Phase ph(gp, AVN_PH_BETA, st);
-    beta_kernel<<<grid, 256, 0, st>>>(W.t, W.z, (int)npad, W.beta, W.fpart);
-    LAUNCH_CHECK("beta_kernel");
+    beta_reduce_kernel<<<grid, 64, 0, st>>>(W.kl, (int)npad, W.beta, W.fpart);
+    LAUNCH_CHECK("beta_reduce_kernel");
   }
   if (want_alpha) {
     Phase ph(gp, AVN_PH_ALPHA, st);

@@ -74,7 +74,9 @@ __device__ __forceinline__ void fprof_event(long long* prof, int type, int k, in
 struct FactorArgs {
   double* L;            // [B][npad][npad]  K on entry (lower block triangle), L on exit
   double* T;            // [B][npad][npad]  T = L^-1 (lower block triangle; diagonal blocks with explicit zeros)
-  double* fpart;        // [B][nb][2]       [.][1] = sum of log L_ii over the block (slot 0 belongs to beta_kernel)
+  double* fpart;        // [B][nb][2]       [.][1] = sum of log L_ii over the block (slot 0 belongs to beta_reduce_kernel)
+  const double* z;      // [B][npad]        converted outputs: beta = T z is formed tile by tile as T is produced
+  double* beta;         // [B][npad]        receives the diagonal-block share T_kk z_k (beta_reduce_kernel adds the rest)
   int32_t* info;        // [B]              first non-positive pivot (1-based) or 0
   int32_t* lflag;       // [B][nb]
   int32_t* tflag;       // [B][nb]
@@ -536,6 +538,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       diag_chol_inv_blocked(sA, sB, s_dval, s_inv, &s_bad, k0, fa.prof);
       FPROF(6);
       FEVENT(0, k, 2);
+      // beta = T z, diagonal-block share: row r of T_kk times z_k (fixed order; off the flags' path: after the publish)
       // T_kk is what the panel and inverse tasks of this step wait for: stored and published first; L_kk itself is
       // read by no task of this kernel and follows behind the flags
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
@@ -553,6 +556,12 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
         double v = log(s_dval[lane]) + log(s_dval[lane + 32]);
         v = warp_sum(v);
         if (lane == 0) fa.fpart[((int64_t)b * nb + k) * 2 + 1] = v;
+      } else if (tid >= 64) {
+        const int r = tid - 64;
+        const double* zk = fa.z + (int64_t)b * npad + k0;
+        double acc = 0.0;
+        for (int c = 0; c <= r; c++) acc = fma(sB[r * FAC_LDS + c], __ldg(zk + c), acc);
+        fa.beta[(int64_t)b * npad + k0 + r] = acc;
       }
       FPROF(5);
     } else if (type == 1) {
@@ -627,6 +636,28 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + jj * 8 + 2 * t;
           *reinterpret_cast<double2*>(Tkj + (int64_t)r * npad + c) = make_double2(-g.acc[ii][jj][0], -g.acc[ii][jj][1]);
         }
+      // beta = T z: this tile's share T[k,j] z_j while the tile is in registers (one pass over T saved).  Each warp sums
+      // its 32 columns; the two column halves go to rows j0 and j0 + 1 of the UNUSED upper tile (j, k) of the L slab, from
+      // where beta_reduce_kernel adds them up in a fixed order.
+      {
+        const double* zj = fa.z + (int64_t)b * npad + j0 + wn * 32 + 2 * t;
+        double zc[4][2];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+          zc[jj][0] = __ldg(zj + jj * 8);
+          zc[jj][1] = __ldg(zj + jj * 8 + 1);
+        }
+        double* part = L + (int64_t)(j0 + wn) * npad + k0;
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) {
+          double sum = 0.0;
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) sum = fma(g.acc[ii][jj][0], zc[jj][0], fma(g.acc[ii][jj][1], zc[jj][1], sum));
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          if (t == 0) part[wm * 32 + ii * 8 + gq] = -sum;
+        }
+      }
       publish(tflag + j, k + 1);
       FPROF(4);
     }
@@ -662,6 +693,28 @@ __global__ void __launch_bounds__(256) beta_kernel(const double* __restrict__ Ta
     q = warp_sum(q);
     if (tid == 0) fpart[((int64_t)b * nb + k) * 2] = q;
   }
+}
+
+// beta = T z from the shares the factor kernel left behind: block row k = diagonal share (in beta) + the shares of the
+// tiles (k, j < k), two column halves each, parked in rows j0, j0 + 1 of the upper tile (j, k) of the L slab; and the
+// block's share of beta^T beta.  grid (nb, B), 64 threads.  Fixed order: deterministic, independent of the schedule.
+__global__ void __launch_bounds__(64) beta_reduce_kernel(const double* __restrict__ Lall, int npad,
+                                                        double* __restrict__ beta_all, double* __restrict__ fpart) {
+  __shared__ double red[2];
+  const int b = blockIdx.y, k = blockIdx.x, r = threadIdx.x, nb = gridDim.x;
+  const double* Lb = Lall + (int64_t)b * npad * npad + k * TILE + r;
+  double s0 = 0.0, s1 = 0.0;
+  for (int j = 0; j < k; j++) {
+    s0 += Lb[(int64_t)(j * TILE) * npad];
+    s1 += Lb[(int64_t)(j * TILE + 1) * npad];
+  }
+  double* beta = beta_all + (int64_t)b * npad + k * TILE + r;
+  const double v = (s0 + s1) + *beta;
+  *beta = v;
+  double q = warp_sum(v * v);
+  if ((r & 31) == 0) red[r >> 5] = q;
+  __syncthreads();
+  if (r == 0) fpart[((int64_t)b * nb + k) * 2] = red[0] + red[1];
 }
 
 }  // namespace avn
