@@ -123,7 +123,7 @@ def flops_factor(N):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE factor_kernel launch of the headline workload (B = 64) from the
 # `ncu --set full` capture summarised in profiles/r01f_ncu_factor_kinv_b64.json
-FACTOR_TRAFFIC_BYTES_B64 = 28.19e9 + 2.20e9
+FACTOR_TRAFFIC_BYTES_B64 = 28.27e9 + 2.23e9
 
 
 def flops_predict(N, d, deg=8):
