@@ -471,3 +471,23 @@ def test_randomised_sweep():
     tool = os.path.join(os.path.dirname(HERE), 'tools', 'fuzz_parity.py')
     r = subprocess.run([sys.executable, tool, '40', '11'], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_packed_host_path_equals_device_path():
+    """GPEngine.loglik_grad_host (pinned upload, one packed device->host copy) returns exactly what the device-tensor
+    path returns, for changing batch sizes (the packed buffers are re-sized) and with a non-PD sample in the batch."""
+    spec = go.ModelSpec(nx=3, kerns=['Matern52'])
+    X, y, th, _ = cases.synth(spec, 90, seed=21)
+    eng = engine(spec)
+    eng.set_data(X, y)
+    rng = np.random.default_rng(0)
+    for B in (1, 5, 2):
+        ths = np.stack([th * np.exp(0.1 * rng.normal(size=th.shape)) for _ in range(B)])
+        if B == 5:
+            ths[3, 0] = -1.0            # negative noise variance: K not positive definite
+        ll, gr, info = eng.loglik_grad(ths)
+        hl, hg, hi = eng.loglik_grad_host(ths)
+        assert np.array_equal(hl, ll.cpu().numpy()) and np.array_equal(hg, gr.cpu().numpy())
+        assert np.array_equal(hi, info.cpu().numpy()) and hi.dtype == np.int32
+        if B == 5:
+            assert hi[3] > 0 and hl[3] == -np.inf and not np.any(hg[3])
