@@ -33,6 +33,9 @@ constexpr int FAC_SPB = TILE / FAC_BK;   // pipeline stages per 64-deep block
 using FacKK = TileGemm<64, 64, FAC_BK, 32, 32, FAC_STAGES, false, false>;
 using FacKR = TileGemm<64, 64, FAC_BK, 32, 32, FAC_STAGES, false, true>;
 constexpr int FAC_THREADS = 128;
+#ifndef AVN_POLL_NS
+#define AVN_POLL_NS 64      // pause between two polls of a progress flag (measured: see DESIGN.md)
+#endif
 constexpr int FAC_LDS = TILE + SPAD;                                 // 68: conflict-free fragment loads both ways
 constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 // two staged 64 x 64 tiles for the epilogues alias the pipeline buffers
@@ -102,7 +105,7 @@ __device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t
   if (threadIdx.x == 0) {
     unsigned spins = 0;
     while (ld_acquire(flag) < need) {
-      __nanosleep(64);
+      __nanosleep(AVN_POLL_NS);
       if ((++spins & 1023u) == 0) {
         if (ld_acquire(ctl + 1) != 0) break;
         if (spins > (1u << 23)) {
@@ -135,7 +138,7 @@ struct SlabWaiter {
         const int va = ld_acquire(fa), vb = ld_acquire(fb);
         have = va < vb ? va : vb;
         if (have >= need) break;
-        __nanosleep(64);
+        __nanosleep(AVN_POLL_NS);
         if ((++spins & 1023u) == 0) {
           if (ld_acquire(ctl + 1) != 0) { have = 0x7fffffff; break; }
           if (spins > (1u << 23)) {
