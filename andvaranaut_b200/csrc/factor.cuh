@@ -233,14 +233,75 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 //       with the pivot chain (shuffle, rsqrt, scale) of step j + 1;
 //   (2) rows below:  x L_pp^T = a  by substitution, one row per thread in registers, L_pp broadcast from shared memory;
 //   (3) rank-16 update of the trailing sub-matrix by DMMA on 8 x 8 fragments of its lower triangle.
-// Inverse: the four T_pp = L_pp^-1 in parallel (one warp each, one column per lane), then block by block
-// T_ij = -T_ii sum_{m=j..i-1} L_im T_mj for block distance 1, 2, 3 by DMMA.
+// Inverse T = L^-1 in 16 x 16 blocks, T_pp = L_pp^-1 (one column per lane) and T_ij = -T_ii sum_{m=j..i-1} L_im T_mj by
+// DMMA.  Block rows 0..2 are produced by warp 1 WHILE warp 0 factors the next panel (the other warps idle there anyway;
+// everything that job reads is final, what it writes nobody else touches); only block row 3 is left for a short tail
+// (warp 0 inverts L_33 while warps 1..3 form the three W_3j, then T_3j = -T_33 W_3j).
 // History (instrumented build, cycles per diagonal task at B = 1, where these tasks ARE the critical path): a
 // register-resident column sweep of the whole block with one __syncthreads per column 85 k; panels with the inverse
-// fused into the warp elimination 52 k; Cholesky first + parallel sub-block inverses 36 k; branch-free steps 30.5 k.
+// fused into the warp elimination 52 k; Cholesky first + parallel sub-block inverses 36 k; branch-free steps 30.5 k;
+// inverse overlapped with the factorisation 24 k.
 // sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T (zeros above the
 // diagonal); dval[j] = L_jj; sinv[j] = 1 / L_jj; *s_bad = first non-positive pivot (1-based, global index).
 // ------------------------------------------------------------------------------------------------
+// ---- warp-level 16 x 16 block operations on the staged tiles (row pitch FAC_LDS), used by the inverse half ----
+// inverse of the lower-triangular sub-block at (c0, c0) of sA into sT: lane c owns column c (forward substitution down
+// the column, two interleaved partial sums); T_cc = sinv[c] = rsqrt(pivot).  One warp; lanes 16..31 shadow 0..15.
+__device__ __forceinline__ void warp_inv16(const double* sA, double* sT, const double* sinv, int c0, int lane) {
+  constexpr int PB = 16;
+  const int c = lane & 15;
+  double tcol[PB];
+#pragma unroll
+  for (int r = 0; r < PB; r++) {
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < r; m++) {
+      const double tm = (m >= c) ? tcol[m] : 0.0;
+      if (m & 1) acc1 = fma(sA[(c0 + r) * FAC_LDS + c0 + m], tm, acc1);
+      else acc0 = fma(sA[(c0 + r) * FAC_LDS + c0 + m], tm, acc0);
+    }
+    const double ir = sinv[c0 + r];
+    tcol[r] = (r == c) ? ir : ((r > c) ? -(acc0 + acc1) * ir : 0.0);
+  }
+  if (lane < PB) {
+#pragma unroll
+    for (int r = 0; r < PB; r++) sT[(c0 + r) * FAC_LDS + c0 + c] = tcol[r];
+  }
+}
+// acc (2 x 2 fragments of 8 x 8) += A(16 x 16 at A) * B(16 x 16 at B), both row-major with pitch FAC_LDS.  One warp.
+__device__ __forceinline__ void warp_mma16(double (&acc)[2][2][2], const double* A, const double* B, int gq, int t) {
+#pragma unroll
+  for (int kk = 0; kk < 16; kk += 4)
+#pragma unroll
+    for (int fi = 0; fi < 2; fi++) {
+      const double a = A[(fi * 8 + gq) * FAC_LDS + kk + t];
+#pragma unroll
+      for (int fj = 0; fj < 2; fj++) dmma884(acc[fi][fj][0], acc[fi][fj][1], a, B[(kk + t) * FAC_LDS + fj * 8 + gq]);
+    }
+}
+__device__ __forceinline__ void warp_store16(double* C, const double (&acc)[2][2][2], double sign, int gq, int t) {
+#pragma unroll
+  for (int fi = 0; fi < 2; fi++)
+#pragma unroll
+    for (int fj = 0; fj < 2; fj++)
+      *reinterpret_cast<double2*>(&C[(fi * 8 + gq) * FAC_LDS + fj * 8 + 2 * t]) =
+          make_double2(sign * acc[fi][fj][0], sign * acc[fi][fj][1]);
+}
+// T_ij = -T_ii sum_{m=j..i-1} L_im T_mj for one off-diagonal 16 x 16 block, by ONE warp (W parked in the destination)
+__device__ __forceinline__ void warp_toff16(const double* sA, double* sT, int bi, int bj, int gq, int t) {
+  constexpr int PB = 16;
+  double w[2][2][2] = {};
+  for (int m = bj; m < bi; m++) warp_mma16(w, sA + (bi * PB) * FAC_LDS + m * PB, sT + (m * PB) * FAC_LDS + bj * PB, gq, t);
+  double* dst = sT + (bi * PB) * FAC_LDS + bj * PB;
+  warp_store16(dst, w, 1.0, gq, t);
+  __syncwarp();
+  double x[2][2][2] = {};
+  warp_mma16(x, sT + (bi * PB) * FAC_LDS + bi * PB, dst, gq, t);
+  __syncwarp();
+  warp_store16(dst, x, -1.0, gq, t);
+  __syncwarp();
+}
+
 // 1 / sqrt(p) for a normal positive p: the hardware estimate (MUFU.RSQ64H, ~2^-22) and one third-order correction
 // y (1 + e/2 + 3 e^2 / 8), e = 1 - p y^2 -- the fast path of the library rsqrt() without its range check and call, so
 // that a whole pivot step stays one basic block and the scheduler can overlap it with the updates of the previous one.
@@ -314,6 +375,22 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
         }
         sinv[c0 + i] = myinv;       // 1 / L_ii (rsqrt of the pivot, as T_ii is defined)
       }
+    } else if (warp >= 2 && p == 0) {
+      // zeros above the diagonal outside the diagonal sub-blocks (L and T): six 16 x 16 blocks that nothing else touches,
+      // filled by the two warps that idle during the first panel
+      for (int e = tid - 64; e < 6 * PB * PB; e += 64) {
+        const int blk = e >> 8, rr = (e >> 4) & 15, cc = e & 15;
+        // blocks (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+        const int br = blk < 3 ? 0 : (blk < 5 ? 1 : 2), bc = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
+        sA[(br * PB + rr) * FAC_LDS + bc * PB + cc] = 0.0;
+        sT[(br * PB + rr) * FAC_LDS + bc * PB + cc] = 0.0;
+      }
+    } else if (warp == 1 && p >= 1) {
+      // the inverse half trails the factorisation by one panel on a warp that would otherwise idle here: everything it
+      // reads (L blocks of rows < p, sinv) is final, everything it writes (T blocks of rows < p) is touched by nobody else
+      warp_inv16(sA, sT, sinv, PB * (p - 1), lane);
+      __syncwarp();
+      for (int bj = p - 2; bj >= 0; bj--) warp_toff16(sA, sT, p - 1, bj, gq, t);
     }
     DPROF(9);
     __syncthreads();
@@ -364,83 +441,28 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
       DPROF(11);
     }
   }
-  // zeros above the diagonal outside the diagonal sub-blocks (L and T)
-  for (int e = tid; e < TILE * TILE; e += FAC_THREADS) {
-    const int r = e >> 6, c = e & 63;
-    if ((c >> 4) > (r >> 4)) {
-      sA[r * FAC_LDS + c] = 0.0;
-      sT[r * FAC_LDS + c] = 0.0;
-    }
-  }
-  // inverses of the four diagonal sub-blocks, one per warp: lane c owns column c of T_pp (forward substitution down
-  // the column, two interleaved partial sums); T_cc = rsqrt(pivot)
+  // tail: only block row 3 of T is left.  warp 0 inverts L_33 while warps 1..3 form W_3j = sum_m L_3m T_mj (j = 0, 1, 2;
+  // every T_mj with m < 3 was finished during the panel loop); then T_3j = -T_33 W_3j.
+  __syncthreads();
   {
-    const int c0 = PB * warp, c = lane & 15;
-    double tcol[PB];
-#pragma unroll
-    for (int r = 0; r < PB; r++) {
-      double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-      for (int m = 0; m < r; m++) {
-        const double tm = (m >= c) ? tcol[m] : 0.0;
-        if (m & 1) acc1 = fma(sA[(c0 + r) * FAC_LDS + c0 + m], tm, acc1);
-        else acc0 = fma(sA[(c0 + r) * FAC_LDS + c0 + m], tm, acc0);
-      }
-      const double ir = sinv[c0 + r];
-      tcol[r] = (r == c) ? ir : ((r > c) ? -(acc0 + acc1) * ir : 0.0);
+    constexpr int LAST = TILE / PB - 1;
+    double w[2][2][2] = {};
+    double* dst = sT + (LAST * PB) * FAC_LDS + (warp - 1) * PB;
+    if (warp == 0) {
+      warp_inv16(sA, sT, sinv, PB * LAST, lane);
+    } else {
+      const int bj = warp - 1;
+      for (int m = bj; m < LAST; m++)
+        warp_mma16(w, sA + (LAST * PB) * FAC_LDS + m * PB, sT + (m * PB) * FAC_LDS + bj * PB, gq, t);
+      warp_store16(dst, w, 1.0, gq, t);
     }
-    if (lane < PB) {
-#pragma unroll
-      for (int r = 0; r < PB; r++) sT[(c0 + r) * FAC_LDS + c0 + c] = tcol[r];
-    }
-  }
-  DPROF(13);
-  // T off the diagonal, by block distance: W = sum_m L_im T_mj, then T_ij = -T_ii W, both on the tensor pipe.
-  // A 16 x 16 block is four 8 x 8 fragments; the (4 - dist) blocks of one distance give 4 (4 - dist) fragments,
-  // dealt round-robin to the warps (at most 3 per warp).
-  for (int dist = 1; dist < TILE / PB; dist++) {
-    const int nfr = 4 * (TILE / PB - dist);
+    DPROF(13);
     __syncthreads();
-    double w0[3], w1[3];
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      const int f = warp + 4 * u;
-      w0[u] = w1[u] = 0.0;
-      if (f < nfr) {
-        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
-        for (int m = bj * PB; m < bi * PB; m += 4)
-          dmma884(w0[u], w1[u], sA[(r0 + gq) * FAC_LDS + m + t], sT[(m + t) * FAC_LDS + q0 + gq]);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      const int f = warp + 4 * u;
-      if (f < nfr) {
-        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
-        *reinterpret_cast<double2*>(&sT[(r0 + gq) * FAC_LDS + q0 + 2 * t]) = make_double2(w0[u], w1[u]);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      const int f = warp + 4 * u;
-      w0[u] = w1[u] = 0.0;
-      if (f < nfr) {
-        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
-#pragma unroll
-        for (int m = 0; m < PB; m += 4)
-          dmma884(w0[u], w1[u], sT[(r0 + gq) * FAC_LDS + bi * PB + m + t], sT[(bi * PB + m + t) * FAC_LDS + q0 + gq]);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      const int f = warp + 4 * u;
-      if (f < nfr) {
-        const int bi = dist + f / 4, bj = bi - dist, r0 = bi * PB + 8 * ((f >> 1) & 1), q0 = bj * PB + 8 * (f & 1);
-        *reinterpret_cast<double2*>(&sT[(r0 + gq) * FAC_LDS + q0 + 2 * t]) = make_double2(-w0[u], -w1[u]);
-      }
+    if (warp != 0) {
+      double x[2][2][2] = {};
+      warp_mma16(x, sT + (LAST * PB) * FAC_LDS + LAST * PB, dst, gq, t);
+      __syncwarp();
+      warp_store16(dst, x, -1.0, gq, t);
     }
   }
   __syncthreads();
