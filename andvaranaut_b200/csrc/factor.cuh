@@ -232,7 +232,9 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 //       is one basic block (branch-free pivot test and rsqrt), so the scheduler overlaps the rank-1 update of step j
 //       with the pivot chain (shuffle, rsqrt, scale) of step j + 1;
 //   (2) rows below:  x L_pp^T = a  by substitution, one row per thread in registers, L_pp broadcast from shared memory;
-//   (3) rank-16 update of the trailing sub-matrix by DMMA on 8 x 8 fragments of its lower triangle.
+//   (3) rank-16 update of the trailing sub-matrix by DMMA on 8 x 8 fragments of its lower triangle, with look-ahead:
+//       only the next diagonal sub-block is updated before the next panel's factorisation starts; the rest of the
+//       update runs beside it on warps 2 and 3.
 // Inverse T = L^-1 in 16 x 16 blocks, T_pp = L_pp^-1 (one column per lane) and T_ij = -T_ii sum_{m=j..i-1} L_im T_mj by
 // DMMA.  Block rows 0..2 are produced by warp 1 WHILE warp 0 factors the next panel (the other warps idle there anyway;
 // everything that job reads is final, what it writes nobody else touches); only block row 3 is left for a short tail
@@ -240,7 +242,7 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
 // History (instrumented build, cycles per diagonal task at B = 1, where these tasks ARE the critical path): a
 // register-resident column sweep of the whole block with one __syncthreads per column 85 k; panels with the inverse
 // fused into the warp elimination 52 k; Cholesky first + parallel sub-block inverses 36 k; branch-free steps 30.5 k;
-// inverse overlapped with the factorisation 24 k.
+// inverse overlapped with the factorisation 27 k; look-ahead trailing update 24 k.
 // sA holds A (lower part) on entry and L (zeros above the diagonal) on exit; sT receives T (zeros above the
 // diagonal); dval[j] = L_jj; sinv[j] = 1 / L_jj; *s_bad = first non-positive pivot (1-based, global index).
 // ------------------------------------------------------------------------------------------------
@@ -300,6 +302,29 @@ __device__ __forceinline__ void warp_toff16(const double* sA, double* sT, int bi
   __syncwarp();
   warp_store16(dst, x, -1.0, gq, t);
   __syncwarp();
+}
+
+// trailing update of panel pp (columns c0 = 16 pp ..): A_rc -= sum_m L_r,c0+m L_c,c0+m on 8 x 8 fragments (fi >= fj) of the
+// lower triangle of the trailing block, fragment pairs numbered row by row; this warp takes pairs q0, q0 + qstep, ... < q1.
+// Pairs 0, 1, 2 are the next diagonal 16 x 16 sub-block.  Conflict-free fragment loads (FAC_LDS).
+__device__ __forceinline__ void syrk_pairs(double* sA, int pp, int q0, int q1, int qstep, int gq, int t) {
+  constexpr int PB = 16;
+  const int c0 = PB * pp, f0 = (c0 + PB) / 8;
+  for (int q = q0; q < q1; q += qstep) {
+    int fi = 0;
+    while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
+    const int fj = q - fi * (fi + 1) / 2;
+    const int r0 = 8 * (f0 + fi), c = 8 * (f0 + fj);
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < PB; kk += 4)
+      dmma884(acc0, acc1, sA[(r0 + gq) * FAC_LDS + c0 + kk + t], sA[(c + gq) * FAC_LDS + c0 + kk + t]);
+    double2* dst = reinterpret_cast<double2*>(&sA[(r0 + gq) * FAC_LDS + c + 2 * t]);
+    double2 cur = *dst;
+    cur.x -= acc0;
+    cur.y -= acc1;
+    *dst = cur;
+  }
 }
 
 // 1 / sqrt(p) for a normal positive p: the hardware estimate (MUFU.RSQ64H, ~2^-22) and one third-order correction
@@ -375,6 +400,11 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
         }
         sinv[c0 + i] = myinv;       // 1 / L_ii (rsqrt of the pivot, as T_ii is defined)
       }
+    } else if (warp >= 2 && p >= 1) {
+      // look-ahead: the previous panel updated only the next diagonal sub-block before this panel's factorisation
+      // started; the rest of its trailing update (rows below that sub-block) runs here, beside warp 0
+      const int nf = TILE / 8 - 2 * p;
+      syrk_pairs(sA, p - 1, 3 + (warp - 2), nf * (nf + 1) / 2, 2, gq, t);
     } else if (warp >= 2 && p == 0) {
       // zeros above the diagonal outside the diagonal sub-blocks (L and T): six 16 x 16 blocks that nothing else touches,
       // filled by the two warps that idle during the first panel
@@ -416,27 +446,9 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
       }
       __syncthreads();
       DPROF(10);
-      // (3) trailing update A_rc -= sum_m L_r,c0+m L_c,c0+m for r >= c >= c1 on the tensor pipe: 8 x 8 fragments
-      // (fi, fj) of the lower triangle, dealt round-robin to the warps; conflict-free fragment loads (FAC_LDS)
-      {
-        const int f0 = c1 / 8, nf = TILE / 8 - f0;          // fragments per side of the trailing block
-        const int npairs = nf * (nf + 1) / 2;
-        for (int q = warp; q < npairs; q += FAC_THREADS / 32) {
-          int fi = 0;
-          while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
-          const int fj = q - fi * (fi + 1) / 2;
-          const int r0 = 8 * (f0 + fi), q0 = 8 * (f0 + fj);
-          double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-          for (int kk = 0; kk < PB; kk += 4)
-            dmma884(acc0, acc1, sA[(r0 + gq) * FAC_LDS + c0 + kk + t], sA[(q0 + gq) * FAC_LDS + c0 + kk + t]);
-          double2* dst = reinterpret_cast<double2*>(&sA[(r0 + gq) * FAC_LDS + q0 + 2 * t]);
-          double2 cur = *dst;
-          cur.x -= acc0;
-          cur.y -= acc1;
-          *dst = cur;
-        }
-      }
+      // (3) trailing update, look-ahead form: only the next diagonal 16 x 16 sub-block (three fragment pairs, one warp
+      // each) stands between this panel and the next factorisation; the rest follows beside it (see above)
+      if (warp < 3) syrk_pairs(sA, p, warp, 3, 3, gq, t);
       __syncthreads();
       DPROF(11);
     }
