@@ -548,19 +548,8 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0 - TILE,
                 [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
         }
-        // block column k-1 is what the whole factorisation waits for (it is published by the panel task of the previous
-        // step): the 64 x 64 tile is fetched in ONE round of loads -- every thread has its sixteen 16-byte loads in flight
-        // at once -- instead of four pipeline slabs issued two at a time (two L2 round trips and four barriers)
-        FEVENT(0, k, 4);
-        wait_flag(lflag + k, k, fa.ctl);
-        FEVENT(0, k, 5);
-        stage_tile(sA, L + (int64_t)k0 * npad + (k0 - TILE), npad);
-        __syncthreads();
-        FEVENT(0, k, 6);
-        if (!idle_quadrant) smem_gemm64x<false>(g.acc, sA, sA, wm, wn, gq, t, TILE);
-        __syncthreads();   // sA is overwritten with the updated block below
-        FPROF(2);
       }
+      // the block as updated so far (A - sum over block columns 0 .. k-2) goes to shared memory ...
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -568,6 +557,36 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
           *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
         }
+      if (k > 0) {
+        // ... and block column k-1, what the whole factorisation waits for (published by the panel task of the previous
+        // step), is applied there: the 64 x 64 tile L[k,k-1] is fetched in ONE round of loads (sixteen 16-byte loads in
+        // flight per thread, instead of four pipeline slabs issued two at a time) and the update runs on the 36 8 x 8
+        // fragments of the lower triangle only, nine per warp (the 32 x 32 quadrant layout of the pipeline computes 48
+        // fragments on three warps)
+        FEVENT(0, k, 4);
+        wait_flag(lflag + k, k, fa.ctl);
+        FEVENT(0, k, 5);
+        stage_tile(sB, L + (int64_t)k0 * npad + (k0 - TILE), npad);
+        __syncthreads();
+        FEVENT(0, k, 6);
+        for (int q = warp; q < 36; q += FAC_THREADS / 32) {
+          int fi = 0;
+          while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
+          const int fj = q - fi * (fi + 1) / 2;
+          double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < TILE; kk += 8) {
+            dmma884(acc0, acc1, sB[(8 * fi + gq) * FAC_LDS + kk + t], sB[(8 * fj + gq) * FAC_LDS + kk + t]);
+            dmma884(acc2, acc3, sB[(8 * fi + gq) * FAC_LDS + kk + 4 + t], sB[(8 * fj + gq) * FAC_LDS + kk + 4 + t]);
+          }
+          double2* dst = reinterpret_cast<double2*>(&sA[(8 * fi + gq) * FAC_LDS + 8 * fj + 2 * t]);
+          double2 cur = *dst;
+          cur.x -= acc0 + acc2;
+          cur.y -= acc1 + acc3;
+          *dst = cur;
+        }
+        FPROF(2);
+      }
       FEVENT(0, k, 1);
       if (tid == 0) s_bad = __ldcg(fa.info + b);
       __syncthreads();
