@@ -647,15 +647,33 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       if (i == k + 1) FEVENT(1, k, 2);
       stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
       __syncthreads();
-      g.zero();
-      smem_gemm64x<false>(g.acc, sA, sB, wm, wn, gq, t, wn == 0 ? 32 : 64);   // X T_kk^T, T_kk lower triangular
+      // X = S T_kk^T on 8 x 8 fragments.  T_kk is lower triangular: the fragment column jf needs k < 8 jf + 8 only.  Warp w
+      // takes the fragment columns w and 7 - w (18 four-deep steps per row fragment between them, the same for every
+      // warp) and all eight row fragments: 144 DMMAs per warp, against 128 / 256 with the 32 x 32 quadrant layout.
+      {
+        double xa[8][2][2];
 #pragma unroll
-      for (int ii = 0; ii < 4; ii++)
+        for (int ii = 0; ii < 8; ii++) xa[ii][0][0] = xa[ii][0][1] = xa[ii][1][0] = xa[ii][1][1] = 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-          *reinterpret_cast<double2*>(Aik + (int64_t)r * npad + c) = make_double2(g.acc[ii][j][0], g.acc[ii][j][1]);
+        for (int c = 0; c < 2; c++) {
+          const int jf = c ? 7 - warp : warp;
+          const int kmax = 8 * jf + 8;
+#pragma unroll 2
+          for (int kk = 0; kk < kmax; kk += 4) {
+            const double bv = sB[(8 * jf + gq) * FAC_LDS + kk + t];
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) dmma884(xa[ii][c][0], xa[ii][c][1], sA[(8 * ii + gq) * FAC_LDS + kk + t], bv);
+          }
         }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int jf = c ? 7 - warp : warp;
+#pragma unroll
+          for (int ii = 0; ii < 8; ii++)
+            *reinterpret_cast<double2*>(Aik + (int64_t)(8 * ii + gq) * npad + 8 * jf + 2 * t) =
+                make_double2(xa[ii][c][0], xa[ii][c][1]);
+        }
+      }
       publish(lflag + i, k + 1);
       if (i == k + 1) FEVENT(1, k, 3);
       FPROF(4);
@@ -682,36 +700,48 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       FPROF(3);
       stage_tile(sA, T + (int64_t)k0 * npad + k0, npad);
       __syncthreads();
-      g.zero();
-      smem_gemm64x<true>(g.acc, sA, sB, wm, wn, gq, t, wm == 0 ? 32 : 64);    // T_kk S, T_kk lower triangular
-      double* Tkj = T + (int64_t)k0 * npad + j0;
-#pragma unroll
-      for (int ii = 0; ii < 4; ii++)
-#pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + jj * 8 + 2 * t;
-          *reinterpret_cast<double2*>(Tkj + (int64_t)r * npad + c) = make_double2(-g.acc[ii][jj][0], -g.acc[ii][jj][1]);
-        }
-      // beta = T z: this tile's share T[k,j] z_j while the tile is in registers (one pass over T saved).  Each warp sums
-      // its 32 columns; the two column halves go to rows j0 and j0 + 1 of the UNUSED upper tile (j, k) of the L slab, from
-      // where beta_reduce_kernel adds them up in a fixed order.
+      // T[k,j] = -T_kk S on 8 x 8 fragments.  T_kk is lower triangular: the fragment row fr needs k < 8 fr + 8 only.  Warp w
+      // takes the fragment rows w and 7 - w (balanced as in the panel tasks) and all eight column fragments.
       {
-        const double* zj = fa.z + (int64_t)b * npad + j0 + wn * 32 + 2 * t;
-        double zc[4][2];
+        double xr[2][8][2];
 #pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-          zc[jj][0] = __ldg(zj + jj * 8);
-          zc[jj][1] = __ldg(zj + jj * 8 + 1);
+        for (int jj = 0; jj < 8; jj++) xr[0][jj][0] = xr[0][jj][1] = xr[1][jj][0] = xr[1][jj][1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int fr = c ? 7 - warp : warp;
+          const int kmax = 8 * fr + 8;
+#pragma unroll 2
+          for (int kk = 0; kk < kmax; kk += 4) {
+            const double av = sA[(8 * fr + gq) * FAC_LDS + kk + t];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) dmma884(xr[c][jj][0], xr[c][jj][1], av, sB[(kk + t) * FAC_LDS + 8 * jj + gq]);
+          }
         }
-        double* part = L + (int64_t)(j0 + wn) * npad + k0;
+        double* Tkj = T + (int64_t)k0 * npad + j0;
+        // beta = T z: this tile's share T[k,j] z_j while the tile is in registers (one pass over T saved).  A warp holds
+        // whole rows of the tile, so one 64-vector per tile goes to row j0 of the UNUSED upper tile (j, k) of the L slab,
+        // from where beta_reduce_kernel adds the shares up in a fixed order.
+        const double* zj = fa.z + (int64_t)b * npad + j0 + 2 * t;
+        double zc[8][2];
 #pragma unroll
-        for (int ii = 0; ii < 4; ii++) {
+        for (int jj = 0; jj < 8; jj++) {
+          zc[jj][0] = __ldg(zj + 8 * jj);
+          zc[jj][1] = __ldg(zj + 8 * jj + 1);
+        }
+        double* part = L + (int64_t)j0 * npad + k0;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int fr = c ? 7 - warp : warp;
           double sum = 0.0;
 #pragma unroll
-          for (int jj = 0; jj < 4; jj++) sum = fma(g.acc[ii][jj][0], zc[jj][0], fma(g.acc[ii][jj][1], zc[jj][1], sum));
+          for (int jj = 0; jj < 8; jj++) {
+            *reinterpret_cast<double2*>(Tkj + (int64_t)(8 * fr + gq) * npad + 8 * jj + 2 * t) =
+                make_double2(-xr[c][jj][0], -xr[c][jj][1]);
+            sum = fma(xr[c][jj][0], zc[jj][0], fma(xr[c][jj][1], zc[jj][1], sum));
+          }
           sum += __shfl_xor_sync(0xffffffffu, sum, 1);
           sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-          if (t == 0) part[wm * 32 + ii * 8 + gq] = -sum;
+          if (t == 0) part[8 * fr + gq] = -sum;
         }
       }
       publish(tflag + j, k + 1);
@@ -752,18 +782,19 @@ __global__ void __launch_bounds__(256) beta_kernel(const double* __restrict__ Ta
 }
 
 // beta = T z from the shares the factor kernel left behind: block row k = diagonal share (in beta) + the shares of the
-// tiles (k, j < k), two column halves each, parked in rows j0, j0 + 1 of the upper tile (j, k) of the L slab; and the
+// tiles (k, j < k), one 64-vector each, parked in row j0 of the upper tile (j, k) of the L slab; and the
 // block's share of beta^T beta.  grid (nb, B), 64 threads.  Fixed order: deterministic, independent of the schedule.
 __global__ void __launch_bounds__(64) beta_reduce_kernel(const double* __restrict__ Lall, int npad,
                                                         double* __restrict__ beta_all, double* __restrict__ fpart) {
   __shared__ double red[2];
   const int b = blockIdx.y, k = blockIdx.x, r = threadIdx.x, nb = gridDim.x;
   const double* Lb = Lall + (int64_t)b * npad * npad + k * TILE + r;
-  double s0 = 0.0, s1 = 0.0;
-  for (int j = 0; j < k; j++) {
+  double s0 = 0.0, s1 = 0.0;   // two interleaved sums over the tiles of the block row (fixed order)
+  for (int j = 0; j + 1 < k; j += 2) {
     s0 += Lb[(int64_t)(j * TILE) * npad];
-    s1 += Lb[(int64_t)(j * TILE + 1) * npad];
+    s1 += Lb[(int64_t)((j + 1) * TILE) * npad];
   }
+  if (k & 1) s0 += Lb[(int64_t)((k - 1) * TILE) * npad];
   double* beta = beta_all + (int64_t)b * npad + k * TILE + r;
   const double v = (s0 + s1) + *beta;
   *beta = v;
