@@ -7,7 +7,6 @@ by a ``concurrent.futures`` process pool (dask is not part of this stack); targe
 GPU hot path either way.
 """
 import multiprocessing as mp
-import os
 from concurrent.futures import ProcessPoolExecutor
 from time import time as stopwatch
 
