@@ -570,16 +570,21 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
       }
       const double* Gm = G + m;
       const double* Dm = ws.dxw + (((int64_t)b * npad) * d + m) * MAXWP + q;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      // eight rows in flight per lane (the loads are strided and L2-latency bound), fixed summation order
+      double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       int n = lane;
-      for (; n + 96 < N; n += 128) {
-        a0 = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a0);
-        a1 = fma(Gm[(int64_t)(n + 32) * d], Dm[(int64_t)(n + 32) * d * MAXWP], a1);
-        a2 = fma(Gm[(int64_t)(n + 64) * d], Dm[(int64_t)(n + 64) * d * MAXWP], a2);
-        a3 = fma(Gm[(int64_t)(n + 96) * d], Dm[(int64_t)(n + 96) * d * MAXWP], a3);
+      for (; n + 224 < N; n += 256) {
+        double gv[8], dv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          gv[u] = Gm[(int64_t)(n + 32 * u) * d];
+          dv[u] = Dm[(int64_t)(n + 32 * u) * d * MAXWP];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) a[u] = fma(gv[u], dv[u], a[u]);
       }
-      for (; n < N; n += 32) a0 = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a0);
-      const double acc = warp_sum((a0 + a1) + (a2 + a3));
+      for (; n < N; n += 32) a[0] = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a[0]);
+      const double acc = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
       if (lane == 0) gr[kd.off_iw + pq] = acc;
     }
   }
@@ -587,9 +592,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   if (kd.n_cw > 0) {
     const double* al = ws.alpha + (int64_t)b * npad;
     for (int q = warp; q < kd.n_cw; q += 8) {
-      double acc = 0.0;
-      for (int n = lane; n < N; n += 32) acc += al[n] * ws.dz[((int64_t)b * npad + n) * MAXWP + q];
-      acc = warp_sum(acc);
+      const double* Dz = ws.dz + (int64_t)b * npad * MAXWP + q;
+      double a[4] = {0.0, 0.0, 0.0, 0.0};
+      int n = lane;
+      for (; n + 96 < N; n += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) a[u] = fma(al[n + 32 * u], Dz[(int64_t)(n + 32 * u) * MAXWP], a[u]);
+      }
+      for (; n < N; n += 32) a[0] = fma(al[n], Dz[(int64_t)n * MAXWP], a[0]);
+      double acc = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
       if (lane == 0) gr[kd.off_cw + q] = -acc + wst[1 + q];
     }
   }
