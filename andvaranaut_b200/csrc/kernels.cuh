@@ -1153,3 +1153,4 @@ __global__ void __launch_bounds__(256) append_kernel(KernDesc kd, int N, int npa
 }  // namespace avn
 
 #include "kinv_fast.cuh"
+#include "kinv_fold.cuh"

@@ -152,6 +152,11 @@ SPECS = {
     'y_warp_a': (go.ModelSpec(nx=2, kerns=['RBF'], ywarp=['affine', 'arcsinh', 'boxcox', 'stdshift']), 120),
     'y_warp_b': (go.ModelSpec(nx=2, kerns=['RBF'], ywarp=['boxcox', 'sinharcsinh', 'stdshift', 'pzero']), 120),
     'y_warp_min': (go.ModelSpec(nx=2, kerns=['Matern52'], ywarp=['meanstd', 'minshift', 'logarithm', 'stddev']), 80),
+    # two-kernel folds take the DMMA gradient epilogue with the product rule (kinv_fold.cuh)
+    'prod_2k': (go.ModelSpec(nx=5, kerns=['RBF', 'Matern52'], ops=['*']), 130),
+    'sum_2k_d16': (go.ModelSpec(nx=16, kerns=['Matern32', 'Matern52'], ops=['+'], noise=False, jitter=1e-4), 191),
+    'prod_2k_xwarp': (go.ModelSpec(nx=3, kerns=['Matern52', 'RBF'], ops=['*'],
+                                   xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0)), None, (['kumaraswamy', 'maxmin'], None)]), 150),
     'both_warps_2k': (go.ModelSpec(nx=4, kerns=['Matern52', 'RBF'], ops=['+'],
                                    xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * 4,
                                    ywarp=['logarithm', 'sal', 'meanstd']), 200),
