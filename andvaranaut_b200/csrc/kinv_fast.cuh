@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
         kern_val_fast<KIND, true>(r2, alpha, kk_, dk_);
         skv = fma(w, kk_, skv);
         wkv[h] = w * kvk * dk_;
+        // Exponential: k' ~ 1/r; the diagonal carries no lengthscale / input gradient ((x_i - x_j) = 0) and would
+        // only amplify the rounding of the gram-form r2_ii
+        if constexpr (KIND == AVN_EXPONENTIAL) wkv[h] = (I == J) ? 0.0 : wkv[h];
         if constexpr (KIND == AVN_RATQUAD) {
           double base = 1.0 + 0.5 * r2 / alpha;
           sal += w * kvk * kk_ * (-log(base) + (0.5 * r2 / alpha) / base);

@@ -1,4 +1,4 @@
-// K3 (two-kernel folds, 'A+B' / 'A*B' of RBF / Matern52 / Matern32): the DMMA epilogue of kinv_fast.cuh with the
+// K3 (two-kernel folds, 'A+B' / 'A*B' without RatQuad): the DMMA epilogue of kinv_fast.cuh with the
 // product rule of the fold (reference: the kernel string parser gpmcmc.py:496-515 and the left-to-right
 // fold gpmcmc.py:282-307).
 //
@@ -150,8 +150,10 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
             const double w0 = w * c0, w1 = w * c1;
             skv0 = fma(w0, k0h[h], skv0);
             skv1 = fma(w1, kq[h], skv1);
-            wk0[h] = w0 * d0h[h];
-            wk1[h] = w1 * kv1 * dq[h];
+            // (x_i - x_j) = 0 on the diagonal: those elements carry no lengthscale / input gradient, and dropping them
+            // keeps the Exponential kernel's k' ~ 1/r from amplifying the rounding of the gram-form r2_ii
+            wk0[h] = (I == J) ? 0.0 : w0 * d0h[h];
+            wk1[h] = (I == J) ? 0.0 : w1 * kv1 * dq[h];
           }
           *pa = make_double2(wk0[0], wk0[1]);
           *pb = make_double2(wk1[0], wk1[1]);
