@@ -495,9 +495,8 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
       if (smem < KinvG2::SMEM_BYTES) smem = KinvG2::SMEM_BYTES;
       rc = launch_kinv_fast(gp, kd.kern[0], gp->has_xwarp, grid, smem, st, kd, (int)gp->N, (int)npad, theta, W);
       if (rc) return rc;
-    } else if (kd.nkern == 2 && kd.kern[0] != AVN_RATQUAD && kd.kern[1] != AVN_RATQUAD) {
-      // two-kernel sum / product: DMMA epilogue with the fold's product rule (kinv_fold.cuh); RatQuad (alpha slot)
-      // stays on the generic kernel
+    } else if (kd.nkern == 2 && !(kd.kern[0] == AVN_RATQUAD && kd.kern[1] == AVN_RATQUAD)) {
+      // two-kernel sum / product: DMMA epilogue with the fold's product rule (kinv_fold.cuh)
       const KinvFoldLayout lay(kd.d);
       size_t smem = (size_t)lay.total * 8;
       if (smem < KinvG2::SMEM_BYTES) smem = KinvG2::SMEM_BYTES;

@@ -1,4 +1,4 @@
-// K3 (two-kernel folds, 'A+B' / 'A*B' without RatQuad): the DMMA epilogue of kinv_fast.cuh with the
+// K3 (two-kernel folds 'A+B' / 'A*B', at most one RatQuad): the DMMA epilogue of kinv_fast.cuh with the
 // product rule of the fold (reference: the kernel string parser gpmcmc.py:496-515 and the left-to-right
 // fold gpmcmc.py:282-307).
 //
@@ -9,7 +9,8 @@
 //              A <- WK_0 = W c_0 kv_0 k_0',   B <- WK_1 = W c_1 kv_1 k_1'
 //   per q      P = WK_q [X_j | 1],  Q = WK_q^T [X_i | 1]  (DMMA)  -> lengthscale slots of kernel q, d ll / d xw
 // The Xs operands (needed for U only) and the [X | 1] operands (needed for P, Q only) share one region, so that
-// two CTAs fit on an SM for every d <= 16.
+// two CTAs fit on an SM for every d <= 16.  Both folds commute, so a RatQuad kernel is always taken in the second pass
+// (qb), where its alpha term has r2 and the fold coefficient at hand.
 #pragma once
 #include "avn_dev.cuh"
 #include "kinv_fast.cuh"
@@ -77,8 +78,10 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
   const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
   const double symw = (ti == tj) ? 1.0 : 2.0;
   const bool mul = kd.op[0] != AVN_ADD;
-  const double kv0 = hyp.kv[0], kv1 = hyp.kv[1];
-  double trw = 0.0, skv0 = 0.0, skv1 = 0.0;
+  const int qa = (kd.kern[0] == AVN_RATQUAD) ? 1 : 0, qb = 1 - qa;   // pass order
+  const double kv0 = hyp.kv[qa], kv1 = hyp.kv[qb], alpha = hyp.alpha;
+  const bool rq = kd.kern[qb] == AVN_RATQUAD;
+  double trw = 0.0, skv0 = 0.0, skv1 = 0.0, sal = 0.0;
 
   for (int e = tid; e < 4 * MAXACC; e += G::NTHREADS) (&wpart[0][0])[e] = 0.0;
   if (tid < TILE) {
@@ -86,10 +89,11 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
     saj[tid] = alpha_all[(int64_t)b * npad + j0 + tid];
   }
 
-  for (int q = 0; q < 2; q++) {
+  for (int p = 0; p < 2; p++) {
+    const int q = p ? qb : qa;
     const double* xs = xs_all + ((int64_t)b * 2 + q) * npad * d;
     const double* x2 = x2_all + ((int64_t)b * 2 + q) * npad;
-    if (q) __syncthreads();   // everyone is done with the operands of kernel 0
+    if (p) __syncthreads();   // everyone is done with the operands of the first pass
     for (int e = tid; e < TILE * lay.dpad; e += G::NTHREADS) {
       int r = e / lay.dpad, m = e % lay.dpad;
       sXsi[r * lay.lds + m] = (m < d) ? xs[(int64_t)(i0 + r) * d + m] : 0.0;
@@ -124,16 +128,16 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-        double kq[2], dq[2];
+        double kq[2], dq[2], r2h[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           double r2 = (sx2i[r] + sx2j[c + h]) - 2.0 * U[i][j][h];
-          r2 = r2 > 0.0 ? r2 : 0.0;
-          kern_val(kind, r2, hyp.alpha, kq[h], dq[h]);
+          r2h[h] = r2 > 0.0 ? r2 : 0.0;
+          kern_val(kind, r2h[h], alpha, kq[h], dq[h]);
         }
         double2* pa = reinterpret_cast<double2*>(&sA[r * LDW + c]);
         double2* pb = reinterpret_cast<double2*>(&sB[r * LDW + c]);
-        if (q == 0) {
+        if (p == 0) {
           *pa = make_double2(kq[0], kq[1]);
           *pb = make_double2(kv0 * dq[0], kv0 * dq[1]);
         } else {
@@ -150,6 +154,10 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
             const double w0 = w * c0, w1 = w * c1;
             skv0 = fma(w0, k0h[h], skv0);
             skv1 = fma(w1, kq[h], skv1);
+            if (rq) {
+              const double base = 1.0 + 0.5 * r2h[h] / alpha;
+              sal += w1 * kv1 * kq[h] * (-log(base) + (0.5 * r2h[h] / alpha) / base);
+            }
             // (x_i - x_j) = 0 on the diagonal: those elements carry no lengthscale / input gradient, and dropping them
             // keeps the Exponential kernel's k' ~ 1/r from amplifying the rounding of the gram-form r2_ii
             wk0[h] = (I == J) ? 0.0 : w0 * d0h[h];
@@ -161,13 +169,17 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
       }
   }
   {
-    const int slot_kv = 2 * d, slot_gv = 2 * d + 2;
+    const int slot_kv = 2 * d, slot_gv = 2 * d + 2, slot_alpha = 2 * d + 3;
     double s = warp_sum(trw);
     if (lane == 0) wpart[warp][slot_gv] = s;
     s = warp_sum(skv0);
-    if (lane == 0) wpart[warp][slot_kv] = s;
+    if (lane == 0) wpart[warp][slot_kv + qa] = s;
     s = warp_sum(skv1);
-    if (lane == 0) wpart[warp][slot_kv + 1] = s;
+    if (lane == 0) wpart[warp][slot_kv + qb] = s;
+    if (rq) {
+      s = warp_sum(sal);
+      if (lane == 0) wpart[warp][slot_alpha] = s;
+    }
   }
   __syncthreads();   // WK tiles complete; the Xs operands are dead
   for (int e = tid; e < TILE * lay.np; e += G::NTHREADS) {
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
       else if (ti != tj) gx = gxpart + (((int64_t)b * nb + ti) * npad + j0 + r) * d;
     }
     for (int m = 0; m < d; m++) {
-      const double il0 = hyp.invl[0][m], il1 = hyp.invl[1][m];
+      const double il0 = hyp.invl[qa][m], il1 = hyp.invl[qb][m];
       const double a0 = il0 * il0, a1 = il1 * il1;
       const double x = sX[r * lay.lda + m], p0 = s0[r * lay.ldp + m], p1 = s1[r * lay.ldp + m];
       double v0 = rowside ? (x * x * RC0 - 2.0 * x * p0) : (x * x * RC0);
@@ -249,8 +261,8 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
       v0 = warp_sum(v0 * a0);
       v1 = warp_sum(v1 * a1);
       if (lane == 0) {
-        wpart[warp][m] = v0;
-        wpart[warp][d + m] = v1;
+        wpart[warp][qa * d + m] = v0;
+        wpart[warp][qb * d + m] = v1;
       }
       if (WITH_GX && gx) gx[m] = (2.0 * a0 * (x * RC0 - p0) + 2.0 * a1 * (x * RC1 - p1)) / symw;
     }

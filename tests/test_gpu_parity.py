@@ -155,6 +155,9 @@ SPECS = {
     # two-kernel folds take the DMMA gradient epilogue with the product rule (kinv_fold.cuh)
     'prod_2k': (go.ModelSpec(nx=5, kerns=['RBF', 'Matern52'], ops=['*']), 130),
     'prod_2k_expo': (go.ModelSpec(nx=4, kerns=['Exponential', 'Matern32'], ops=['*']), 140),
+    'sum_2k_rq_first': (go.ModelSpec(nx=3, kerns=['RatQuad', 'RBF'], ops=['+']), 100),   # passes swapped
+    'prod_2k_rq': (go.ModelSpec(nx=6, kerns=['Matern52', 'RatQuad'], ops=['*'],
+                                xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] + [None] * 5), 129),
     'sum_2k_d16': (go.ModelSpec(nx=16, kerns=['Matern32', 'Matern52'], ops=['+'], noise=False, jitter=1e-4), 191),
     'prod_2k_xwarp': (go.ModelSpec(nx=3, kerns=['Matern52', 'RBF'], ops=['*'],
                                    xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0)), None, (['kumaraswamy', 'maxmin'], None)]), 150),
