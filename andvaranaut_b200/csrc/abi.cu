@@ -502,17 +502,23 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
       if (smem < KinvG2::SMEM_BYTES) smem = KinvG2::SMEM_BYTES;
       static size_t opted_fold = 0;
       if (smem > opted_fold) {
-        e = opt_in_smem(kinv_grad_fold2_kernel<false>, smem);
-        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<true>, smem);
+        e = opt_in_smem(kinv_grad_fold2_kernel<false, false>, smem);
+        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<true, false>, smem);
+        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<false, true>, smem);
+        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<true, true>, smem);
         if (e != cudaSuccess) return fail_cuda("kinv_grad_fold2 smem opt-in", e);
         opted_fold = smem;
       }
-      if (gp->has_xwarp)
-        kinv_grad_fold2_kernel<true><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.t, W.alpha,
-                                                                         W.xw, W.xs, W.x2, W.gpart, W.gxpart);
-      else
-        kinv_grad_fold2_kernel<false><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.t, W.alpha,
-                                                                          W.xw, W.xs, W.x2, W.gpart, W.gxpart);
+      const bool rq = kd.kern[0] == AVN_RATQUAD || kd.kern[1] == AVN_RATQUAD;
+#define AVN_FOLD2(GX, RQ)                                                                                              \
+  kinv_grad_fold2_kernel<GX, RQ><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, \
+                                                                       W.xw, W.xs, W.x2, W.gpart, W.gxpart)
+      if (gp->has_xwarp) {
+        if (rq) AVN_FOLD2(true, true); else AVN_FOLD2(true, false);
+      } else {
+        if (rq) AVN_FOLD2(false, true); else AVN_FOLD2(false, false);
+      }
+#undef AVN_FOLD2
     } else if (gp->has_xwarp) {
       kinv_grad_kernel<true><<<grid, KinvG::NTHREADS, KinvG::SMEM_BYTES, st>>>(
           kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, W.xw, W.gpart, W.gxpart);

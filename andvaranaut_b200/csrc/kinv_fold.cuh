@@ -36,7 +36,9 @@ struct KinvFoldLayout {
   }
 };
 
-template <bool WITH_GX>
+// RQ: one of the two kernels is RatQuad (its own instantiation keeps the alpha term and the pass swap out of the
+// common one)
+template <bool WITH_GX, bool RQ>
 __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
     KernDesc kd, int N, int npad, const double* __restrict__ theta, const double* __restrict__ Tall,
     const double* __restrict__ alpha_all, const double* __restrict__ xw_all, const double* __restrict__ xs_all,
@@ -78,9 +80,8 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
   const int wm = warp % G::WARPS_M, wn = warp / G::WARPS_M, gq = lane >> 2, t = lane & 3;
   const double symw = (ti == tj) ? 1.0 : 2.0;
   const bool mul = kd.op[0] != AVN_ADD;
-  const int qa = (kd.kern[0] == AVN_RATQUAD) ? 1 : 0, qb = 1 - qa;   // pass order
+  const int qa = (RQ && kd.kern[0] == AVN_RATQUAD) ? 1 : 0, qb = 1 - qa;   // pass order
   const double kv0 = hyp.kv[qa], kv1 = hyp.kv[qb], alpha = hyp.alpha;
-  const bool rq = kd.kern[qb] == AVN_RATQUAD;
   double trw = 0.0, skv0 = 0.0, skv1 = 0.0, sal = 0.0;
 
   for (int e = tid; e < 4 * MAXACC; e += G::NTHREADS) (&wpart[0][0])[e] = 0.0;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
             const double w0 = w * c0, w1 = w * c1;
             skv0 = fma(w0, k0h[h], skv0);
             skv1 = fma(w1, kq[h], skv1);
-            if (rq) {
+            if constexpr (RQ) {
               const double base = 1.0 + 0.5 * r2h[h] / alpha;
               sal += w1 * kv1 * kq[h] * (-log(base) + (0.5 * r2h[h] / alpha) / base);
             }
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 2) kinv_grad_fold2_kernel(
     if (lane == 0) wpart[warp][slot_kv + qa] = s;
     s = warp_sum(skv1);
     if (lane == 0) wpart[warp][slot_kv + qb] = s;
-    if (rq) {
+    if constexpr (RQ) {
       s = warp_sum(sal);
       if (lane == 0) wpart[warp][slot_alpha] = s;
     }
