@@ -75,6 +75,7 @@ SYMBOLS = {
     'avn_gp_append': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p]),
     'avn_gp_last_launch_count': (C.c_int64, [C.c_void_p]),
+    'avn_gp_set_debug': (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     'avn_gp_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'avn_gp_phase_ms': (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }

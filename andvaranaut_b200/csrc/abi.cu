@@ -29,6 +29,12 @@ struct avn_gp {
   int64_t launches = 0;
   bool has_xwarp = false;
   bool profiling = false;
+  int device = -1;                    // CUDA device the handle is bound to (current device at avn_gp_create, or at the
+                                      // first call that enqueues work when no device was visible at create time)
+  bool dev_ready = false;             // shared-memory opt-ins / occupancy of this handle's kernels done on `device`
+  int fac_resident = 0;               // CTAs of the persistent factor kernel that are resident at once on `device`
+  unsigned max_spins = 1u << 26;      // bound of the factor kernel's flag waits, in polls (avn_gp_set_debug)
+  int fault = 0;                      // fault injection for tests (avn_gp_set_debug)
   int max_groups = 1;                 // independent sample groups on internal streams (avn_gp_set_streams)
   cudaStream_t gstream[8] = {};
   cudaEvent_t gev[9] = {};            // [0]: fork point on the caller's stream, [1+g]: join of group g
@@ -52,6 +58,35 @@ struct Phase {
     }
   }
 };
+// Every entry point that enqueues work runs with the handle's device current and restores the caller's on exit, so a
+// handle may be used from any host thread (new threads start on device 0) and several handles on several devices may
+// share one process.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DevGuard(avn_gp* gp) {
+    err = cudaGetDevice(&prev);
+    if (err != cudaSuccess) return;
+    if (gp->device < 0) gp->device = prev;
+    if (gp->device != prev) {
+      err = cudaSetDevice(gp->device);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DevGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+static int ensure_ready(avn_gp* gp);
+#define ENTER_DEVICE(gp)                                              \
+  DevGuard dev_guard__(gp);                                           \
+  if (dev_guard__.err != cudaSuccess) return fail_cuda("device", dev_guard__.err); \
+  if (!(gp)->dev_ready) {                                             \
+    int rc__ = ensure_ready(gp);                                      \
+    if (rc__) return rc__;                                            \
+  }
+
 static void phases_reset(avn_gp* gp) {
   for (int i = 0; i < AVN_PH_COUNT; i++) gp->ev_used[i] = false;
 }
@@ -122,12 +157,16 @@ extern "C" int avn_gp_create(const avn_model_desc* desc, avn_gp** out) {
   kd.off_alpha = p;
   if (kd.has_alpha) p += 1;
   kd.P = p;
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess) gp->device = dev;   // no device visible (CPU-only symbol checks): bound later
+  else (void)cudaGetLastError();
   *out = gp;
   return 0;
 }
 
 extern "C" void avn_gp_destroy(avn_gp* gp) {
   if (!gp) return;
+  DevGuard guard(gp);
   for (auto& e : gp->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : gp->gev)
@@ -137,8 +176,18 @@ extern "C" void avn_gp_destroy(avn_gp* gp) {
   delete gp;
 }
 
+extern "C" int avn_gp_set_debug(avn_gp* gp, int wait_bound_log2, int fault) {
+  if (!gp) return fail("avn_gp_set_debug: null handle");
+  if (wait_bound_log2 < 10 || wait_bound_log2 > 31) return fail("avn_gp_set_debug: wait_bound_log2 out of range [10,31]");
+  if (fault < 0 || fault > 1) return fail("avn_gp_set_debug: unknown fault");
+  gp->max_spins = wait_bound_log2 >= 31 ? 0x7fffffffu : (1u << wait_bound_log2);
+  gp->fault = fault;
+  return 0;
+}
+
 extern "C" int avn_gp_set_profiling(avn_gp* gp, int enable) {
   if (!gp) return fail("avn_gp_set_profiling: null handle");
+  DevGuard guard(gp);
   if (enable && !gp->ev[0]) {
     for (auto& e : gp->ev) {
       cudaError_t err = cudaEventCreate(&e);
@@ -151,6 +200,7 @@ extern "C" int avn_gp_set_profiling(avn_gp* gp, int enable) {
 
 extern "C" int avn_gp_phase_ms(avn_gp* gp, double* out_ms) {
   if (!gp || !out_ms) return fail("avn_gp_phase_ms: null argument");
+  DevGuard guard(gp);
   for (int i = 0; i < AVN_PH_COUNT; i++) {
     out_ms[i] = 0.0;
     if (gp->profiling && gp->ev_used[i]) {
@@ -247,6 +297,62 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
     gp->launches++;                                         \
   } while (0)
 
+// dynamic shared memory of the kernels whose request depends on the model (d, nkern)
+static size_t cov_smem_bytes(const KernDesc& kd) { return (size_t)(2 * kd.nkern * TILE * kd.d + 2 * kd.nkern * TILE) * 8; }
+static size_t kinv_fast_smem_bytes(const KernDesc& kd) {
+  const KinvFastLayout lay(kd.d);
+  const size_t smem = (size_t)lay.total * 8;
+  return smem < KinvG2::SMEM_BYTES ? KinvG2::SMEM_BYTES : smem;
+}
+static size_t kinv_fold_smem_bytes(const KernDesc& kd) {
+  const KinvFoldLayout lay(kd.d);
+  const size_t smem = (size_t)lay.total * 8;
+  return smem < KinvG2::SMEM_BYTES ? KinvG2::SMEM_BYTES : smem;
+}
+static size_t kxs_smem_bytes(const KernDesc& kd) { return (size_t)(kd.nkern * TILE * (kd.d | 1) + kd.nkern * TILE) * 8; }
+static size_t predict_grad_smem_bytes(const KernDesc& kd) { return kxs_smem_bytes(kd) + (size_t)(4 * TILE * 2 * kd.d) * 8; }
+
+static int launch_kinv_fast(bool optin_only, int kind, bool gx, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd,
+                            int N, int npad, const double* theta, const WsPtrs& W);
+
+// Once per handle, on the handle's device (the caller holds a DevGuard): every shared-memory opt-in this model's
+// kernels need and the resident CTA count of the persistent factor kernel.  cudaFuncSetAttribute is per device, so the
+// result lives in the handle -- no process-wide caches -- and nothing of this is left on the per-call path.
+static int ensure_ready(avn_gp* gp) {
+  const KernDesc& kd = gp->kd;
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  if (cov_smem_bytes(kd) > 48 * 1024) chk(opt_in_smem(cov_kernel, cov_smem_bytes(kd)));
+  chk(opt_in_smem(factor_kernel, FAC_SMEM_BYTES));
+  if (kd.nkern == 1) {
+    WsPtrs none{};
+    int rc = launch_kinv_fast(true, kd.kern[0], gp->has_xwarp, dim3(1), kinv_fast_smem_bytes(kd), nullptr, kd, 0, 0, nullptr, none);
+    if (rc) return rc;
+  } else if (kd.nkern == 2 && !(kd.kern[0] == AVN_RATQUAD && kd.kern[1] == AVN_RATQUAD)) {
+    const size_t smem = kinv_fold_smem_bytes(kd);
+    chk(opt_in_smem(kinv_grad_fold2_kernel<false, false>, smem));
+    chk(opt_in_smem(kinv_grad_fold2_kernel<true, false>, smem));
+    chk(opt_in_smem(kinv_grad_fold2_kernel<false, true>, smem));
+    chk(opt_in_smem(kinv_grad_fold2_kernel<true, true>, smem));
+  } else {
+    chk(opt_in_smem(kinv_grad_kernel<false>, KinvG::SMEM_BYTES));
+    chk(opt_in_smem(kinv_grad_kernel<true>, KinvG::SMEM_BYTES));
+  }
+  chk(opt_in_smem(predict_var_kernel, PredG::SMEM_BYTES));
+  chk(opt_in_smem(predict_v_kernel, PredG::SMEM_BYTES));
+  chk(opt_in_smem(ttv_kernel, TtvG::SMEM_BYTES));
+  if (predict_grad_smem_bytes(kd) > 48 * 1024) chk(opt_in_smem(predict_grad_kernel, predict_grad_smem_bytes(kd)));
+  if (e != cudaSuccess) return fail_cuda("shared-memory opt-in", e);
+  int sms = 0, per_sm = 0;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gp->device);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES);
+  if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
+  gp->fac_resident = sms * per_sm;
+  if (const char* env = getenv("AVN_FAC_CTAS_PER_SM")) gp->fac_resident = sms * atoi(env);   // development knob
+  gp->dev_ready = true;
+  return 0;
+}
+
 // conversions + scaled inputs for B samples
 static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st) {
   Phase ph(gp, AVN_PH_WARP, st);
@@ -263,11 +369,7 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
   Phase ph(gp, AVN_PH_COV, st);
   const KernDesc& kd = gp->kd;
   const int64_t nb = npad / TILE, ntiles = nb * (nb + 1) / 2;
-  size_t smem = (size_t)(2 * kd.nkern * TILE * kd.d + 2 * kd.nkern * TILE) * 8;
-  if (smem > 48 * 1024) {
-    cudaError_t e = opt_in_smem(cov_kernel, smem);
-    if (e != cudaSuccess) return fail_cuda("cov_kernel smem", e);
-  }
+  const size_t smem = cov_smem_bytes(kd);   // opted in by ensure_ready when above 48 KB
   const dim3 grid((unsigned)ntiles, (unsigned)B);
   if (kd.nkern == 1 && smem <= 48 * 1024) {
     // single-kernel models: instantiation per kernel kind (no switch / fold inside the element loop)
@@ -286,22 +388,10 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
   return 0;
 }
 
-// Persistent grid of the factor kernel: as many CTAs as fit on the device at once (3 per SM), never more than tasks.
-static int factor_grid(int64_t total_tasks, int* out) {
-  static int resident = 0;
-  if (!resident) {
-    cudaError_t e = opt_in_smem(factor_kernel, FAC_SMEM_BYTES);
-    if (e != cudaSuccess) return fail_cuda("factor smem opt-in", e);
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES);
-    if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
-    resident = sms * per_sm;
-    if (const char* e = getenv("AVN_FAC_CTAS_PER_SM")) resident = sms * atoi(e);   // development knob
-  }
-  *out = (int)(total_tasks < resident ? total_tasks : resident);
-  return 0;
+// Persistent grid of the factor kernel: as many CTAs as fit on the handle's device at once (3 per SM; counted by
+// ensure_ready), never more than tasks.
+static int factor_grid(const avn_gp* gp, int64_t total_tasks) {
+  return (int)(total_tasks < gp->fac_resident ? total_tasks : gp->fac_resident);
 }
 
 // Cholesky K -> L in place (kl) and T = L^-1 (t): one persistent dataflow launch (factor.cuh).
@@ -311,13 +401,13 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   const int nb = (int)(npad / TILE);
   const int64_t total = B * nb * nb;
   if (total > 0x7fffffffLL) return fail("run_factor: B * (N/64)^2 exceeds the task counter");
-  int grid = 0;
-  int rc = factor_grid(total, &grid);
-  if (rc) return rc;
+  const int grid = factor_grid(gp, total);
   FactorArgs fa;
   fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info; fa.z = W.z; fa.beta = W.beta;
   fa.lflag = W.lflag; fa.tflag = W.tflag; fa.ctl = W.ctl;
   fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.n = (int)gp->N; fa.want_inverse = want_inverse ? 1 : 0;
+  fa.max_spins = gp->max_spins;
+  fa.fault = gp->fault;
   fa.dgap = 0;   // D(.,s+1) right behind P(.,s,s+1): its first s slabs are final already, only the last one waits
   fa.prof = nullptr;
 #ifdef AVN_FACTOR_PROF
@@ -398,6 +488,7 @@ extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double
   avn_ws_layout L;
   layout(gp, B, &L);
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_cov: workspace too small");
+  ENTER_DEVICE(gp);
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -430,27 +521,26 @@ static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& 
   return p;
 }
 
+// optin_only: the shared-memory opt-in of this instantiation (ensure_ready), no launch
 template <int KIND, bool GX>
-static int launch_kinv_fast_t(dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd, int N, int npad,
+static int launch_kinv_fast_t(bool optin_only, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd, int N, int npad,
                               const double* theta, const WsPtrs& W) {
-  static size_t opted = 0;
-  if (smem > opted) {
+  if (optin_only) {
     cudaError_t e = opt_in_smem(kinv_grad_fast_kernel<KIND, GX>, smem);
     if (e != cudaSuccess) return fail_cuda("kinv_grad_fast smem opt-in", e);
-    opted = smem;
+    return 0;
   }
   kinv_grad_fast_kernel<KIND, GX><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, N, npad, theta, W.t, W.alpha, W.xw, W.xs, W.x2,
                                                                         W.gpart, W.gxpart);
   return 0;
 }
 
-static int launch_kinv_fast(avn_gp* gp, int kind, bool gx, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd,
+static int launch_kinv_fast(bool optin_only, int kind, bool gx, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd,
                             int N, int npad, const double* theta, const WsPtrs& W) {
-  (void)gp;
-#define AVN_DISPATCH(K)                                                                     \
-  case K:                                                                                   \
-    return gx ? launch_kinv_fast_t<K, true>(grid, smem, st, kd, N, npad, theta, W)          \
-              : launch_kinv_fast_t<K, false>(grid, smem, st, kd, N, npad, theta, W);
+#define AVN_DISPATCH(K)                                                                           \
+  case K:                                                                                         \
+    return gx ? launch_kinv_fast_t<K, true>(optin_only, grid, smem, st, kd, N, npad, theta, W)    \
+              : launch_kinv_fast_t<K, false>(optin_only, grid, smem, st, kd, N, npad, theta, W);
   switch (kind) {
     AVN_DISPATCH(AVN_RBF)
     AVN_DISPATCH(AVN_MATERN52)
@@ -479,36 +569,16 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
   rc = run_beta_alpha(gp, Bg, W, npad, want_grad, st);
   if (rc) return rc;
   if (want_grad) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      e = opt_in_smem(kinv_grad_kernel<false>, KinvG::SMEM_BYTES);
-      if (e == cudaSuccess) e = opt_in_smem(kinv_grad_kernel<true>, KinvG::SMEM_BYTES);
-      if (e != cudaSuccess) return fail_cuda("kinv_grad smem opt-in", e);
-      attr_done = true;
-    }
     Phase ph(gp, AVN_PH_KINV_GRAD, st);
     const dim3 grid((unsigned)ntiles, (unsigned)Bg);
     if (kd.nkern == 1) {
       // single-kernel model: DMMA epilogue specialised on the kernel kind
-      const KinvFastLayout lay(kd.d);
-      size_t smem = (size_t)lay.total * 8;
-      if (smem < KinvG2::SMEM_BYTES) smem = KinvG2::SMEM_BYTES;
-      rc = launch_kinv_fast(gp, kd.kern[0], gp->has_xwarp, grid, smem, st, kd, (int)gp->N, (int)npad, theta, W);
+      rc = launch_kinv_fast(false, kd.kern[0], gp->has_xwarp, grid, kinv_fast_smem_bytes(kd), st, kd, (int)gp->N, (int)npad,
+                            theta, W);
       if (rc) return rc;
     } else if (kd.nkern == 2 && !(kd.kern[0] == AVN_RATQUAD && kd.kern[1] == AVN_RATQUAD)) {
       // two-kernel sum / product: DMMA epilogue with the fold's product rule (kinv_fold.cuh)
-      const KinvFoldLayout lay(kd.d);
-      size_t smem = (size_t)lay.total * 8;
-      if (smem < KinvG2::SMEM_BYTES) smem = KinvG2::SMEM_BYTES;
-      static size_t opted_fold = 0;
-      if (smem > opted_fold) {
-        e = opt_in_smem(kinv_grad_fold2_kernel<false, false>, smem);
-        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<true, false>, smem);
-        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<false, true>, smem);
-        if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fold2_kernel<true, true>, smem);
-        if (e != cudaSuccess) return fail_cuda("kinv_grad_fold2 smem opt-in", e);
-        opted_fold = smem;
-      }
+      const size_t smem = kinv_fold_smem_bytes(kd);
       const bool rq = kd.kern[0] == AVN_RATQUAD || kd.kern[1] == AVN_RATQUAD;
 #define AVN_FOLD2(GX, RQ)                                                                                              \
   kinv_grad_fold2_kernel<GX, RQ><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.t, W.alpha, \
@@ -554,6 +624,7 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
   avn_ws_layout L;
   layout(gp, B, &L);
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_loglik_grad: workspace too small");
+  ENTER_DEVICE(gp);
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -625,8 +696,11 @@ extern "C" size_t avn_gp_state_bytes(const avn_gp* gp) {
   return (size_t)state_layout(gp).total;
 }
 
-__global__ void hyp_store_kernel(KernDesc kd, const double* __restrict__ theta, HypS* __restrict__ out) {
+// also the abort check of avn_gp_factorize: a timed-out wait of the factor kernel (ctl[1] != 0) becomes info = -1
+__global__ void hyp_store_kernel(KernDesc kd, const double* __restrict__ theta, HypS* __restrict__ out,
+                                 const int32_t* __restrict__ ctl, int32_t* __restrict__ info) {
   __shared__ HypS h;
+  if (threadIdx.x == 0 && ctl[1] != 0) info[0] = -1;
   for (int e = threadIdx.x; e < (int)(sizeof(HypS) / 8); e += blockDim.x) reinterpret_cast<double*>(&h)[e] = 0.0;
   __syncthreads();
   load_hyp(h, kd, theta);
@@ -647,6 +721,7 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
   StateLayout S = state_layout(gp);
   if (ws_bytes < (size_t)L.total) return fail("avn_gp_factorize: workspace too small");
   if (state_bytes < (size_t)S.total) return fail("avn_gp_factorize: state buffer too small");
+  ENTER_DEVICE(gp);
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -670,7 +745,7 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
   if (rc) return rc;
   rc = run_beta_alpha(gp, 1, W, npad, true, st);
   if (rc) return rc;
-  hyp_store_kernel<<<1, 128, 0, st>>>(gp->kd, theta_dev, reinterpret_cast<HypS*>(sb + S.hyp));
+  hyp_store_kernel<<<1, 128, 0, st>>>(gp->kd, theta_dev, reinterpret_cast<HypS*>(sb + S.hyp), W.ctl, info_dev);
   LAUNCH_CHECK("hyp_store_kernel");
   return 0;
 }
@@ -711,6 +786,7 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   const int ns = row_split(M, npad);
   const int64_t cols_cap = (int64_t)(ws_bytes / ((npad + (ns > 1 ? 2 * ns : 0)) * 8)) / TILE * TILE;
   if (cols_cap < TILE) return fail("avn_gp_predict: workspace too small");
+  ENTER_DEVICE(gp);
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -721,13 +797,7 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   const double* x2 = reinterpret_cast<const double*>(sb + S.x2);
   const double* T = reinterpret_cast<const double*>(sb + S.t);
   double* Kxs = static_cast<double*>(ws_dev);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = opt_in_smem(predict_var_kernel, PredG::SMEM_BYTES);
-    if (e != cudaSuccess) return fail_cuda("predict smem opt-in", e);
-    attr_done = true;
-  }
-  const size_t smem_kxs = (size_t)(kd.nkern * TILE * (kd.d | 1) + kd.nkern * TILE) * 8;
+  const size_t smem_kxs = kxs_smem_bytes(kd);
   for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
     const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
     const unsigned nblk = (unsigned)(cols / TILE);
@@ -780,6 +850,7 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
   const int64_t per_col = 2 * npad + (ns > 1 ? (int64_t)ns * (2 + 2 * kd.d) : 0);
   const int64_t cols_cap = (int64_t)(ws_bytes / (per_col * 8)) / TILE * TILE;
   if (cols_cap < TILE) return fail("avn_gp_predict_grad: workspace too small");
+  ENTER_DEVICE(gp);
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -789,19 +860,8 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
   const double* xs = reinterpret_cast<const double*>(sb + S.xs);
   const double* x2 = reinterpret_cast<const double*>(sb + S.x2);
   const double* T = reinterpret_cast<const double*>(sb + S.t);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = opt_in_smem(predict_v_kernel, PredG::SMEM_BYTES);
-    if (e == cudaSuccess) e = opt_in_smem(ttv_kernel, TtvG::SMEM_BYTES);
-    if (e != cudaSuccess) return fail_cuda("predict_grad smem opt-in", e);
-    attr_done = true;
-  }
-  const size_t smem_kxs = (size_t)(kd.nkern * TILE * (kd.d | 1) + kd.nkern * TILE) * 8;
-  const size_t smem_pg = smem_kxs + (size_t)(4 * TILE * 2 * kd.d) * 8;
-  if (smem_pg > 48 * 1024) {
-    cudaError_t e = opt_in_smem(predict_grad_kernel, smem_pg);
-    if (e != cudaSuccess) return fail_cuda("predict_grad_kernel smem", e);
-  }
+  const size_t smem_kxs = kxs_smem_bytes(kd);
+  const size_t smem_pg = predict_grad_smem_bytes(kd);   // opted in by ensure_ready when above 48 KB
   avn_epilogue latent = *epi;
   latent.mode = 0;
   for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
@@ -863,6 +923,7 @@ extern "C" int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, co
   StateLayout S = state_layout(gp);
   if (state_bytes < (size_t)S.total) return fail("avn_gp_append: state buffer too small");
   if (ws_bytes < avn_gp_append_workspace_bytes(gp)) return fail("avn_gp_append: workspace too small");
+  ENTER_DEVICE(gp);
   gp->launches = 0;
   phases_reset(gp);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -88,6 +88,8 @@ struct FactorArgs {
   int n;                // valid rows (N <= npad): tiles of the last block row skip their padding fragments
   int want_inverse;     // 0: skip the R tasks (log-likelihood only)
   int dgap;             // slots between P(.,s,s+1) and the look-ahead D(.,s+1)
+  unsigned max_spins;   // bound of every flag wait in polls (avn_gp_set_debug; default 2^26, several seconds)
+  int fault;            // fault injection (tests): 1 = the panel task P(0,0,1) never publishes its flag
   long long* prof;      // AVN_FACTOR_PROF builds: 8 cycle counters (ticket, wait, gemm, wait T_kk, epilogue, diag, -, -)
 };
 
@@ -100,15 +102,17 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// thread 0 polls until *flag >= need (bounded: ~1 s, then the abort flag ends every later wait at once)
-__device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t* ctl) {
+// thread 0 polls until *flag >= need.  Bounded: after max_spins polls the abort flag ctl[1] is raised, which ends every
+// later wait at once; finalize_kernel / abort_check_kernel turn it into info = -1 (results invalid), so a timed-out wait
+// is reported, never returned as data.
+__device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t* ctl, unsigned max_spins) {
   if (threadIdx.x == 0) {
     unsigned spins = 0;
     while (ld_acquire(flag) < need) {
       __nanosleep(AVN_POLL_NS);
       if ((++spins & 1023u) == 0) {
         if (ld_acquire(ctl + 1) != 0) break;
-        if (spins > (1u << 23)) {
+        if (spins > max_spins) {
           atomicExch(ctl + 1, 1);
           break;
         }
@@ -127,6 +131,7 @@ struct SlabWaiter {
   int32_t* ctl;
   int* s_known;
   int m0, known;
+  unsigned max_spins;
   __device__ __forceinline__ void operator()(int kt) {
     if (kt % FAC_SPB) return;
     const int need = m0 + kt / FAC_SPB + 1;
@@ -141,7 +146,7 @@ struct SlabWaiter {
         __nanosleep(AVN_POLL_NS);
         if ((++spins & 1023u) == 0) {
           if (ld_acquire(ctl + 1) != 0) { have = 0x7fffffff; break; }
-          if (spins > (1u << 23)) {
+          if (spins > max_spins) {
             atomicExch(ctl + 1, 1);
             have = 0x7fffffff;
             break;
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
         const bool idle_quadrant = (wm == 0 && wn == 1);
         if (k > 1) {
           // block columns 0 .. k-2 of row k through the pipeline: final long before this task is on the critical path
-          SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0};
+          SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins};
           g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0 - TILE,
                 [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
         }
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
         // fragments of the lower triangle only, nine per warp (the 32 x 32 quadrant layout of the pipeline computes 48
         // fragments on three warps)
         FEVENT(0, k, 4);
-        wait_flag(lflag + k, k, fa.ctl);
+        wait_flag(lflag + k, k, fa.ctl, fa.max_spins);
         FEVENT(0, k, 5);
         stage_tile(sB, L + (int64_t)k0 * npad + (k0 - TILE), npad);
         __syncthreads();
@@ -628,7 +633,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       FacKK g;
       load_neg_tile(g.acc, Aik, npad, wm, wn, gq, t);
       if (k > 0) {
-        SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0};
+        SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins};
         g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
               [&](int kt) { w(kt); });
         FPROF(2);
@@ -642,7 +647,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
         }
       FPROF(4);
       if (i == k + 1) FEVENT(1, k, 1);
-      wait_flag(lflag + k, k + 1, fa.ctl);   // T[k,k] is there (also orders the sA writes)
+      wait_flag(lflag + k, k + 1, fa.ctl, fa.max_spins);   // T[k,k] is there (also orders the sA writes)
       FPROF(3);
       if (i == k + 1) FEVENT(1, k, 2);
       stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
@@ -674,6 +679,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
                 make_double2(xa[ii][c][0], xa[ii][c][1]);
         }
       }
+      if (fa.fault == 1 && b == 0 && k == 0 && i == 1) continue;   // injected fault: this tile is never published
       publish(lflag + i, k + 1);
       if (i == k + 1) FEVENT(1, k, 3);
       FPROF(4);
@@ -683,7 +689,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       const int j = idx, j0 = j * TILE;
       FacKR g;
       g.zero();
-      SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0};
+      SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0, fa.max_spins};
       // first slab: B = T[j,j] is lower triangular, its columns n >= 32 vanish for the first 32 k
       g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
             [&](int kt) { w(kt); }, wn == 1 ? 32 / FAC_BK : 0);
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           *reinterpret_cast<double2*>(&sB[r * FAC_LDS + c]) = make_double2(g.acc[ii][jj][0], g.acc[ii][jj][1]);
         }
       FPROF(4);
-      wait_flag(lflag + k, k + 1, fa.ctl);
+      wait_flag(lflag + k, k + 1, fa.ctl, fa.max_spins);
       FPROF(3);
       stage_tile(sA, T + (int64_t)k0 * npad + k0, npad);
       __syncthreads();

@@ -512,14 +512,23 @@ __global__ void __launch_bounds__(256) gx_reduce_kernel(int npad, int d, double*
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs progs, int N, int npad, int ntiles,
                                                        int want_grad, const double* __restrict__ theta, WsPtrs ws,
-                                                       const int32_t* __restrict__ info, double* __restrict__ ll,
+                                                       int32_t* __restrict__ info, double* __restrict__ ll,
                                                        double* __restrict__ grad) {
   __shared__ double slots[MAXACC];
   const int b = blockIdx.x, tid = threadIdx.x;
   const double* th = theta + (int64_t)b * kd.P;
   const double* wst = ws.wstat + (int64_t)b * WSTAT;
-  const bool bad = info[b] != 0;
-  if (tid == 0) {
+  // a wait of the factor kernel timed out (factor.cuh): nothing downstream of it can be trusted.  Reported as
+  // info = -1 with ll = NaN and a zero gradient -- distinct from a non-positive pivot (info > 0, ll = -inf).
+  const bool aborted = ws.ctl[1] != 0;
+  const bool bad = aborted || info[b] != 0;
+  if (aborted) {
+    __syncthreads();   // every thread has read info[b]
+    if (tid == 0) {
+      info[b] = -1;
+      ll[b] = NAN;
+    }
+  } else if (tid == 0) {
     const double norm = -0.5 * N * 1.8378770664093454835606594728112;  // log(2 pi)
     const int nbk = npad / TILE;
     const double* fp = ws.fpart + (int64_t)b * nbk * 2;

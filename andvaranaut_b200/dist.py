@@ -47,7 +47,10 @@ class Shard:
             dev = getattr(engine, 'device', 'cpu')
             packed = torch.zeros(0, P + 2, dtype=torch.float64, device=dev)
         full = self._gather_rows(packed, per, B).cpu().numpy()
-        return full[:, 0], full[:, 1:1 + P].copy(), full[:, 1 + P].astype(np.int32)
+        info = full[:, 1 + P].astype(np.int32)
+        if np.any(info < 0):       # a rank's factor kernel aborted (include/avn_gp.h): every rank sees it and raises
+            raise RuntimeError('avn_gp_loglik_grad: factorisation aborted on the device (info = -1) on at least one rank')
+        return full[:, 0], full[:, 1:1 + P].copy(), info
 
     def predict(self, engine, Xs, **kw):
         """Xs [M,d] (identical on every rank) -> (mean [M], var [M]) numpy on every rank; blocks of test points are

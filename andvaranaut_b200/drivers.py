@@ -41,6 +41,8 @@ class Posterior:
         else:
             ll_t, g_t, info_t = self.engine.loglik_grad(theta)
             ll, gll, info = ll_t.cpu().numpy(), g_t.cpu().numpy(), info_t.cpu().numpy()
+            if np.any(info < 0):
+                raise RuntimeError('avn_gp_loglik_grad: factorisation aborted on the device (info = -1)')
         self.n_eval += z.shape[0]
         self.n_calls += 1
         lp, glp = self.space.prior(theta)
@@ -92,12 +94,17 @@ class _Rendezvous:
     def _flush(self):
         ids = sorted(self.pending)
         z = np.stack([self.pending[i] for i in ids])
-        v, g, _ = self.post.logp_dlogp(z, jacobian=False)
-        for k, i in enumerate(ids):
-            self.results[i] = (v[k], g[k])
-        self.pending.clear()
-        self.gen += 1
-        self.cv.notify_all()
+        try:
+            v, g, _ = self.post.logp_dlogp(z, jacobian=False)
+            for k, i in enumerate(ids):
+                self.results[i] = (v[k], g[k])
+        except BaseException as e:   # device / collective failure: every waiting optimiser gets it, nobody is left waiting
+            for i in ids:
+                self.results[i] = e
+        finally:
+            self.pending.clear()
+            self.gen += 1
+            self.cv.notify_all()
 
     def evaluate(self, i, z):
         with self.cv:
@@ -107,8 +114,12 @@ class _Rendezvous:
             else:
                 gen = self.gen
                 while self.gen == gen:
-                    self.cv.wait()
-            return self.results.pop(i)
+                    if not self.cv.wait(timeout=600.0):
+                        raise RuntimeError('batched evaluation did not arrive within 600 s')
+            r = self.results.pop(i)
+            if isinstance(r, BaseException):
+                raise r
+            return r
 
     def leave(self):
         with self.cv:
@@ -127,6 +138,7 @@ def find_map_multi(post, z0s, maxeval=5000, method='L-BFGS-B', **kwargs):
         return z[None, :], np.array([v])
     rv = _Rendezvous(post, R)
     out = [None] * R
+    errors = []
 
     def run(i):
         n = [0]
@@ -144,8 +156,10 @@ def find_map_multi(post, z0s, maxeval=5000, method='L-BFGS-B', **kwargs):
             zi = minimize(cost, zi, method=method, jac=True, **kwargs).x
         except StopIteration:
             pass
-        except Exception as e:  # a failed restart must not block the others (gpmcmc.py:337-339)
-            print('Restart failed', e)
+        except (ValueError, FloatingPointError, np.linalg.LinAlgError) as e:
+            print('Restart failed', e)       # a numerically failed restart must not block the others (gpmcmc.py:337-339)
+        except BaseException as e:           # device errors end the whole fit: re-raised by the caller below
+            errors.append(e)
         finally:
             rv.leave()
         out[i] = zi
@@ -155,6 +169,8 @@ def find_map_multi(post, z0s, maxeval=5000, method='L-BFGS-B', **kwargs):
         t.start()
     for t in threads:
         t.join()
+    if errors:
+        raise errors[0]
     zs = np.stack(out)
     v, _, _ = post.logp_dlogp(zs, jacobian=False)
     return zs, v

@@ -6,6 +6,7 @@ reference (``pm.Model()`` built in ``GPMCMC.__fit``, andvaranaut/gpmcmc.py:185-3
 a noise flag, optional learnable input/output warps and the training data.
 """
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -18,12 +19,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
 class GPError(RuntimeError):
     pass
+
+
+def _on_device(fn):
+    """Run an engine method with the engine's device current (the calling thread's current device is restored
+    afterwards): buffers, the stream handed to the library and the library's launches all belong to ``self.device``
+    whatever thread or current device the call comes from (new host threads start on device 0)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
+def check_info(info, what='avn_gp'):
+    """info < 0 = the device aborted the factorisation (a dataflow wait timed out, include/avn_gp.h): an error, never
+    data.  ``info`` is a host array or scalar."""
+    if np.any(np.asarray(info) < 0):
+        raise GPError(f'{what}: factorisation aborted on the device (a progress-flag wait of the factor kernel timed out; '
+                      'the results are invalid) -- is another process time-slicing this GPU?')
 
 
 class GPEngine:
@@ -63,7 +79,8 @@ class GPEngine:
             self.n_cw = desc.ywarp.nparams
         self._desc = desc
         h = C.c_void_p()
-        rc = self.lib.avn_gp_create(C.byref(desc), C.byref(h))
+        with torch.cuda.device(self.device):       # the handle is bound to the device current at create
+            rc = self.lib.avn_gp_create(C.byref(desc), C.byref(h))
         if rc != 0:
             raise GPError(_lib.last_error())
         self._h = h
@@ -84,6 +101,14 @@ class GPEngine:
                 pass
             self._h = None
 
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_debug(self, wait_bound_log2=26, fault=0):
+        """wait bound of the factor kernel's flag waits (2^k polls) and fault injection (tests)."""
+        if self.lib.avn_gp_set_debug(self._h, int(wait_bound_log2), int(fault)) != 0:
+            raise GPError(_lib.last_error())
+
     def set_streams(self, max_groups):
         if self.lib.avn_gp_set_streams(self._h, int(max_groups)) != 0:
             raise GPError(_lib.last_error())
@@ -92,6 +117,7 @@ class GPEngine:
         if self.lib.avn_gp_set_profiling(self._h, 1 if enable else 0) != 0:
             raise GPError(_lib.last_error())
 
+    @_on_device
     def phase_ms(self):
         """elapsed milliseconds per phase of the most recent call (synchronises on its last event)."""
         out = (C.c_double * len(_lib.PHASES))()
@@ -124,6 +150,7 @@ class GPEngine:
             return a.to(device=self.device, dtype=torch.float64).contiguous()
         return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
 
+    @_on_device
     def set_data(self, X, y, _keep_state=False):
         X = self._dev(X)
         y = self._dev(y).reshape(-1)
@@ -140,6 +167,7 @@ class GPEngine:
     def npad(self):
         return (self.N + _lib.AVN_TILE - 1) // _lib.AVN_TILE * _lib.AVN_TILE
 
+    @_on_device
     def _workspace(self, B):
         need = self.lib.avn_gp_workspace_bytes(self._h, B)
         if need == 0:
@@ -155,6 +183,7 @@ class GPEngine:
         return max(1, int(budget_bytes // per))
 
     # -- hot path ----------------------------------------------------------------------------
+    @_on_device
     def loglik_grad(self, theta, want_grad=True, out=None):
         """theta [B,P] (constrained).  Returns (ll [B], grad [B,P] or None, info [B]) device tensors."""
         theta = self._dev(theta)
@@ -171,13 +200,14 @@ class GPEngine:
         else:
             ll, grad, info = out
         rc = self.lib.avn_gp_loglik_grad(self._h, _ptr(theta), B, _ptr(ll), _ptr(grad), _ptr(info), _ptr(ws),
-                                         ws.numel(), _stream())
+                                         ws.numel(), self._stream())
         if rc != 0:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         self._last_B = B
         return ll, grad, info
 
+    @_on_device
     def loglik_grad_host(self, theta):
         """host arrays in, host arrays out: theta [B,P] NumPy -> (ll [B], grad [B,P], info [B]) NumPy.  The three results
         live in ONE device buffer and come back with one device->host copy (the optimiser / sampler drivers call this
@@ -194,10 +224,13 @@ class GPEngine:
         self._theta_host.copy_(torch.from_numpy(theta))
         self.loglik_grad(self._theta_host.to(self.device, non_blocking=True), out=out)
         self._pack_host.copy_(buf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         h = self._pack_host.numpy()
-        return h[:B].copy(), h[B:B + B * P].reshape(B, P).copy(), h[B + B * P:].view(np.int32)[:B].copy()
+        info = h[B + B * P:].view(np.int32)[:B].copy()
+        check_info(info, 'avn_gp_loglik_grad')
+        return h[:B].copy(), h[B:B + B * P].reshape(B, P).copy(), info
 
+    @_on_device
     def cov(self, theta):
         theta = self._dev(theta)
         if theta.ndim == 1:
@@ -205,12 +238,13 @@ class GPEngine:
         B = theta.shape[0]
         ws = self._workspace(B)
         K = torch.empty(B, self.npad, self.npad, dtype=torch.float64, device=self.device)
-        rc = self.lib.avn_gp_cov(self._h, _ptr(theta), B, _ptr(K), _ptr(ws), ws.numel(), _stream())
+        rc = self.lib.avn_gp_cov(self._h, _ptr(theta), B, _ptr(K), _ptr(ws), ws.numel(), self._stream())
         if rc != 0:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         return K
 
+    @_on_device
     def debug_buffers(self, B=None):
         """views of the named workspace buffers of the last loglik_grad call (tests / profiling)."""
         B = B or self._last_B
@@ -235,6 +269,7 @@ class GPEngine:
         return out
 
     # -- predict -----------------------------------------------------------------------------
+    @_on_device
     def factorize(self, theta):
         theta = self._dev(theta).reshape(-1)
         if theta.shape[0] != self.P:
@@ -245,13 +280,14 @@ class GPEngine:
             self._state = torch.empty(sb, dtype=torch.uint8, device=self.device)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         rc = self.lib.avn_gp_factorize(self._h, _ptr(theta), _ptr(self._state), self._state.numel(), _ptr(info),
-                                       _ptr(ws), ws.numel(), _stream())
+                                       _ptr(ws), ws.numel(), self._stream())
         if rc != 0:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         self._theta_fact = theta
         return info
 
+    @_on_device
     def append(self, xnew, znew):
         """Extend the factorised state by one converted training point (hyperparameters unchanged): O(N^2) rank-1
         update of T = L^-1 and alpha in place (``avn_gp_append``); a full refactorisation only when the padded slab
@@ -272,7 +308,7 @@ class GPEngine:
             self._pws = torch.empty(need, dtype=torch.uint8, device=self.device)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         rc = self.lib.avn_gp_append(self._h, _ptr(self._state), self._state.numel(), _ptr(xnew), _ptr(znew), _ptr(info),
-                                    _ptr(self._pws), self._pws.numel(), _stream())
+                                    _ptr(self._pws), self._pws.numel(), self._stream())
         if rc < 0:
             raise GPError(_lib.last_error())
         if rc == 1:                       # slab full: npad grows, new layout
@@ -313,6 +349,7 @@ class GPEngine:
         cols = min((M + _lib.AVN_TILE - 1) // _lib.AVN_TILE * _lib.AVN_TILE, 148 * 64 * 2)
         return full // cols * _lib.AVN_TILE
 
+    @_on_device
     def predict(self, Xs, epilogue=None, mean_add=None, max_ws_bytes=4 << 30):
         """Xs [M,nx] converted test points -> (mean [M], var [M]) device tensors."""
         if self._state is None:
@@ -331,12 +368,13 @@ class GPEngine:
         var = torch.empty(M, dtype=torch.float64, device=self.device)
         madd = self._dev(mean_add).reshape(-1) if mean_add is not None else None
         rc = self.lib.avn_gp_predict(self._h, _ptr(self._state), _ptr(Xs), M, C.byref(epi), _ptr(madd), _ptr(mean),
-                                     _ptr(var), _ptr(self._pws), self._pws.numel(), _stream())
+                                     _ptr(var), _ptr(self._pws), self._pws.numel(), self._stream())
         if rc != 0:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         return mean, var
 
+    @_on_device
     def predict_grad(self, Xs, epilogue=None, mean_add=None, dmean_add=None, pred_noise=True, max_ws_bytes=4 << 30):
         """Xs [M,nx] converted query points -> (mean [M], var [M], dmean [M,nx], dvar [M,nx]) device tensors: the
         predictive graph of the BO refine step (gpmcmc.py:738-801) with its gradient w.r.t. the query points.
@@ -361,7 +399,7 @@ class GPEngine:
         dmadd = self._dev(dmean_add).reshape(M, self.nx) if dmean_add is not None else None
         rc = self.lib.avn_gp_predict_grad(self._h, _ptr(self._state), _ptr(Xs), M, C.byref(epi), 1 if pred_noise else 0,
                                           _ptr(madd), _ptr(dmadd), _ptr(mean), _ptr(var), _ptr(dmean), _ptr(dvar),
-                                          _ptr(self._pws), self._pws.numel(), _stream())
+                                          _ptr(self._pws), self._pws.numel(), self._stream())
         if rc != 0:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)

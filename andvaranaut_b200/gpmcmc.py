@@ -315,10 +315,10 @@ class GPMCMC(LHC):
                 mp = space.hypers_dict(z)
             else:
                 mp = self.map_extract(data)
-                try:
+                try:       # the reference's polish may fail numerically (gpmcmc.py:356-361); device errors propagate
                     z, _, _ = find_map(post, space.initial_z(mp), maxeval=maxeval)
                     mp = space.hypers_dict(z)
-                except Exception:
+                except (ValueError, FloatingPointError, np.linalg.LinAlgError):
                     pass
         else:
             raise Exception('method must be one of map, mcmc_map, or mcmc_mean')
@@ -358,34 +358,47 @@ class GPMCMC(LHC):
         conrevs, model or hypers change (the reference refactorises and recompiles on every call, :588-598)."""
         if self.hypers is None:
             raise Exception('Error: model must be fitted before predicting')
-        key = (jitter, len(self.xc))
-        if self._pred_cache is not None and self._pred_cache[0] == key:
-            return self._pred_cache[1], self._pred_cache[2]
-        if self._pred_cache is not None and self._pred_cache[0][0] == jitter \
-                and 0 < len(self.xc) - self._pred_cache[0][1] <= 64:
-            # points were appended (BO / inverse_opt / fit_method='none') under unchanged hypers and conversions:
-            # rank-1 extension of the cached factorisation, O(N^2) per point (SURVEY 8f.3)
-            (_, n0), eng, th = self._pred_cache
-            ok = True
-            for i in range(n0, len(self.xc)):
-                if int(eng.append(self.xc[i], self.yc[i, 0])[0]) != 0:
-                    ok = False
-                    break
-            if ok:
-                self._pred_cache = (key, eng, th)
-                return eng, th
-            self._pred_cache = None
-        from .gp import GPEngine
-        eng = GPEngine(nx=self.nx, kerns=self.kerns, ops=self.ops, noise=self.noise, jitter=jitter, device=self.device)
-        eng.set_data(self.xc, self.yc[:, 0])
+        from .gp import GPEngine, check_info
         space = ParamSpace(self.nx, self.nkern, self.noise, has_alpha='RatQuad' in self.kerns)
         th = space.theta_from_hypers(self.hypers)
-        info = eng.factorize(th)
-        if int(info[0]) != 0:
-            raise Exception(f'Error: covariance matrix not positive definite at pivot {int(info[0])}')
+        n = len(self.xc)
+        c = self._pred_cache
+        # the cache is valid for exactly the state it was built from: jitter, the hyperparameter VALUES (the reference
+        # passes point=self.hypers on every call, so edited / loaded hypers must take effect) and the converted data
+        # (a checksum of xc / yc catches in-place edits at unchanged length)
+        if c is not None and c['jitter'] == jitter and np.array_equal(c['theta'], th):
+            n0 = c['n']
+            if n0 <= n and n - n0 <= 64 and c['sum'] == self.__data_sum(n0):
+                if n == n0:
+                    return c['eng'], th
+                # points were appended (BO / inverse_opt / fit_method='none') under unchanged hypers and conversions:
+                # rank-1 extension of the cached factorisation, O(N^2) per point (SURVEY 8f.3)
+                eng, ok = c['eng'], True
+                for i in range(n0, n):
+                    info = int(eng.append(self.xc[i], self.yc[i, 0])[0])
+                    check_info(info, 'avn_gp_append')
+                    if info != 0:
+                        ok = False
+                        break
+                if ok:
+                    c.update(n=n, sum=self.__data_sum(n))
+                    return eng, th
+        self._pred_cache = None
+        eng = GPEngine(nx=self.nx, kerns=self.kerns, ops=self.ops, noise=self.noise, jitter=jitter, device=self.device)
+        eng.set_data(self.xc, self.yc[:, 0])
+        info = int(eng.factorize(th)[0])
+        check_info(info, 'avn_gp_factorize')
+        if info != 0:
+            raise Exception(f'Error: covariance matrix not positive definite at pivot {info}')
         self.gp = eng
-        self._pred_cache = (key, eng, th)
+        self._pred_cache = dict(jitter=jitter, theta=th.copy(), n=n, sum=self.__data_sum(n), eng=eng)
         return eng, th
+
+    def __data_sum(self, n):
+        """order-dependent checksum of the first n converted training rows (bit patterns, so -0.0 / NaN edits count)."""
+        import zlib
+        return (zlib.crc32(np.ascontiguousarray(self.xc[:n]).view(np.uint8)),
+                zlib.crc32(np.ascontiguousarray(self.yc[:n, 0]).view(np.uint8)))
 
     def predict(self, x, return_var=False, convert=True, revert=True, normvar=False, jitter=1e-6, EI=False,
                 EIopt=None, deg=8):
@@ -597,8 +610,11 @@ class GPMCMC(LHC):
             self.xopt = self.x[xoptf(self.y[:, 0]), :]
             self.yopt = yoptf(self.y)
             if fit_method == 'map':
-                try:
+                from .gp import GPError
+                try:       # warm start at the previous hypers; the reference retries from the default start (:897-904)
                     self.fit(method=fit_method, iwgp=iwgp, cwgp=cwgp, jitter=jitter, start=self.hypers)
+                except GPError:
+                    raise
                 except Exception:
                     self.fit(method=fit_method, iwgp=iwgp, cwgp=cwgp, jitter=jitter)
             else:
@@ -688,7 +704,7 @@ class GPMCMC(LHC):
             try:
                 z, _, _ = find_map(post, post.space.initial_z(mp), maxeval=maxeval)
                 mp = post.space.hypers_dict(z)
-            except Exception:
+            except (ValueError, FloatingPointError, np.linalg.LinAlgError):
                 pass
         return data, mp
 
@@ -705,20 +721,21 @@ class GPMCMC(LHC):
         call returning value and analytic gradient; otherwise bounded L-BFGS-B where each gradient is ONE batched
         predict of 2 nx + 1 points (central differences)."""
         from scipy.optimize import minimize
-        if acq is not None:
+        if acq is not None and acq(xsamp) is not None:
+            # device errors (GPError) propagate: only numerical trouble of the host optimiser falls through to the
+            # finite-difference polish below
             try:
-                if acq(xsamp) is not None:
-                    def potential(x):
-                        f, g = acq(x)
-                        return -f, -g
-                    post = XPosterior(self.priors, potential)
-                    z0 = post.space.z_from_theta(np.clip(xsamp[0], lbs, ubs))
-                    f0 = post.logp_dlogp(z0[None, :], False)[0][0]
-                    z, f1, _ = find_map(post, z0, maxeval=200)
-                    if np.isfinite(f1) and f1 >= f0:
-                        return post.space.theta_from_z(z[None, :])[0]
-                    return xsamp
-            except Exception:
+                def potential(x):
+                    f, g = acq(x)
+                    return -f, -g
+                post = XPosterior(self.priors, potential)
+                z0 = post.space.z_from_theta(np.clip(xsamp[0], lbs, ubs))
+                f0 = post.logp_dlogp(z0[None, :], False)[0][0]
+                z, f1, _ = find_map(post, z0, maxeval=200)
+                if np.isfinite(f1) and f1 >= f0:
+                    return post.space.theta_from_z(z[None, :])[0]
+                return xsamp
+            except (ValueError, FloatingPointError, np.linalg.LinAlgError):
                 pass
         span = ubs - lbs
 
@@ -734,7 +751,7 @@ class GPMCMC(LHC):
                            options=dict(maxiter=50))
             if np.isfinite(res.fun) and res.fun <= optf(xsamp)[0]:
                 return np.array([res.x])
-        except Exception:
+        except (ValueError, FloatingPointError, np.linalg.LinAlgError):
             pass
         return xsamp
 
@@ -773,8 +790,11 @@ class GPMCMC(LHC):
         hyp = dict(self.hypers)
         hyp['gv'] = float(noise_t)
         th = space.theta_from_hypers(hyp)
+        from .gp import check_info
         ll, _, info = eng.loglik_grad(th, want_grad=False)
-        if int(info[0]) != 0 or int(eng.factorize(th)[0]) != 0:
+        infos = (int(info[0]), int(eng.factorize(th)[0]))
+        check_info(infos, 'inverse_posterior')
+        if infos != (0, 0):
             raise Exception('Error: covariance matrix not positive definite')
         c = self.yconrevs[0]
         yfull = np.r_[self.y[:, 0], yobs[:, 0]]

@@ -14,11 +14,23 @@
  * Conventions
  *   - plain C: pointers and sizes only, no C++/torch types; every *_dev pointer is DEVICE memory owned
  *     by the caller; the library allocates nothing on the device and never frees caller memory.
+ *     (One exception: a library built with -DAVN_FACTOR_PROF, an instrumentation build that is never shipped,
+ *     keeps one small static counter buffer of its own.)
  *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*) and is asynchronous;
- *     only avn_gp_create/avn_gp_destroy touch no stream.
+ *     only avn_gp_create/avn_gp_destroy/avn_gp_set_data touch no stream.
+ *   - a handle is bound to ONE device: the device that is current when avn_gp_create runs (or, when none is
+ *     visible then, when the first call that enqueues work runs).  Every such call makes that device current for
+ *     its duration and restores the caller's afterwards, so handles may be used from any host thread and handles
+ *     on different devices may share a process; the stream and every *_dev pointer must belong to the handle's
+ *     device.  Per-device kernel attributes are set once per handle, not cached process-wide.
  *   - return value: 0 = ok, negative = bad argument / launch failure (text via avn_last_error()).
  *     Numerical failure is DATA, not an error: info[b] = k > 0 means pivot k of sample b was not
  *     positive; then ll[b] = -inf and grad[b,:] = 0 (PyMC's NaN-Cholesky -> -inf convention).
+ *     info[b] = -1 means the factorisation was ABORTED: a dataflow wait inside the persistent factor kernel
+ *     exceeded its bound (several seconds by default; reachable under time-slicing with another process, a
+ *     debugger or a sanitizer).  Then ll[b] = NaN, grad[b,:] = 0 (avn_gp_factorize: the state buffer is invalid)
+ *     and the call must be repeated; the bound is set with avn_gp_set_debug.  The calls are asynchronous, so the
+ *     abort cannot be a return code: callers that read info must treat a negative value as an error.
  *   - all arithmetic is FP64.
  *
  * Hyperparameter vector theta (constrained space, one row per sample), in this order
@@ -104,7 +116,11 @@ void avn_gp_destroy(avn_gp* gp);
 int avn_gp_num_params(const avn_gp* gp);
 
 /* training data: X [N,d] row-major (columns with a learnable warp RAW, the others already converted),
- * y [N] (raw, mean-subtracted when the output warp is learnable, else already converted). */
+ * y [N] (raw, mean-subtracted when the output warp is learnable, else already converted).
+ * Registers the two pointers and N in the handle; no device work is enqueued, hence no stream argument (SURVEY 8b
+ * sketched one for a copy that this library does not make: it allocates no device memory to copy into).  Lifetime:
+ * the caller keeps both arrays alive and unchanged until the next avn_gp_set_data / avn_gp_destroy; every later
+ * call reads them on ITS stream, so they must be complete on that stream when it is made. */
 int avn_gp_set_data(avn_gp* gp, const double* X_dev, const double* y_dev, int64_t N);
 
 size_t avn_gp_workspace_bytes(const avn_gp* gp, int64_t B);
@@ -157,6 +173,11 @@ int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const double* Xs_dev,
 size_t avn_gp_append_workspace_bytes(const avn_gp* gp);
 int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, const double* xnew_dev, const double* znew_dev,
                   int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Test / diagnosis knobs of the persistent factor kernel.  wait_bound_log2 in [10,31]: every progress-flag wait gives
+ * up after 2^wait_bound_log2 polls (default 26, several seconds) and the call reports info = -1.  fault = 1 injects a
+ * fault -- the panel tile P(0,0,1) of sample 0 is never published -- so that tests can exercise that path; 0 = none. */
+int avn_gp_set_debug(avn_gp* gp, int wait_bound_log2, int fault);
 
 /* introspection used by bench.py: number of kernel launches issued by the last call on this handle */
 int64_t avn_gp_last_launch_count(const avn_gp* gp);

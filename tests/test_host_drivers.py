@@ -338,3 +338,36 @@ def test_gpmcmc_pickles_without_device_state(tmp_path):
     assert h.gp is None and h._pred_cache is None and h.shard is None
     assert np.array_equal(h.x, g.x) and np.array_equal(h.yc, g.yc) and np.array_equal(h.hypers['l'], g.hypers['l'])
     assert g.gp is not None       # the live object keeps its device state
+
+
+def test_batched_restarts_propagate_an_evaluation_failure_without_hanging():
+    """a device / collective error inside the batched evaluation reaches every optimiser thread and ends the fit with
+    that error (the rendezvous used to leave the other threads waiting forever)."""
+    class Boom(RuntimeError):
+        pass
+
+    class FailingPosterior:
+        def __init__(self):
+            self.n = 0
+
+        def logp_dlogp(self, z, jacobian):
+            self.n += 1
+            if self.n == 3:
+                raise Boom('device lost')
+            z = np.atleast_2d(z)
+            return -0.5 * np.sum(z * z, axis=1), -z, np.zeros(len(z), dtype=np.int32)
+
+    import threading
+    res = {}
+
+    def run():
+        try:
+            drivers.find_map_multi(FailingPosterior(), np.random.default_rng(0).normal(size=(4, 3)))
+            res['out'] = 'returned'
+        except Boom as e:
+            res['out'] = e
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    t.join(timeout=60)
+    assert not t.is_alive(), 'find_map_multi hung after a failed evaluation'
+    assert isinstance(res['out'], Boom)
