@@ -281,15 +281,15 @@ def test_appended_points_extend_the_cached_factorisation(tmp_path):
     g = tutorial_gp(tmp_path, kernel='Matern52', noise=True, n=50)
     g.fit()
     g.predict(g.x[:3])                       # factorise + cache
-    eng0 = g._pred_cache[1]
+    eng0 = g._pred_cache['eng']
     g.BO(opt_type='min', max_iter=3, method='EI', fit_method='none', predict_samps=500, seed=1, refine=False)
     assert len(g.x) == 53
     xq = np.column_stack([np.linspace(0.1, 1.9, 25), np.linspace(1.05, 1.45, 25)])
     m1, v1 = g.predict(xq, return_var=True)
-    assert g._pred_cache[1] is eng0 and eng0.N == 53          # same engine, extended in place
+    assert g._pred_cache['eng'] is eng0 and eng0.N == 53          # same engine, extended in place
     g._pred_cache = None
     m2, v2 = g.predict(xq, return_var=True)                   # refactorised from scratch
-    assert g._pred_cache[1] is not eng0
+    assert g._pred_cache['eng'] is not eng0
     assert np.max(np.abs(m1 - m2)) <= 1e-8 * np.max(np.abs(m2))
     assert np.max(np.abs(v1 - v2)) <= 1e-8 * np.max(np.abs(v2)) + 1e-12
 

@@ -3,9 +3,9 @@
 Tolerances (BASELINE.json north_star): log-likelihood and gradient relative 1e-9, predictive
 mean relative 1e-8, predictive variance |d var| <= 1e-8 * max(|var|, kv) (variance is a cancelling
 difference).  Gradient components are compared relative to max(|g_i|, 1e-3 |g|_inf).
-Cases whose cond(K) makes two CPU evaluations of the reference formula disagree above those
-tolerances (RBF, noise=False, jitter 1e-6: cond ~ 6e9) are checked against cond(K)*eps instead,
-and say so.
+The one case whose cond(K) makes two float64 evaluations of the reference formula disagree above those
+tolerances (C1: RBF, noise=False, jitter 1e-6, cond ~ 6e9) is held to the oracle's own error against a
+50-digit truth (oracle/gp_truth.py) instead, and says so.
 """
 import os
 import sys
@@ -65,22 +65,27 @@ def test_golden_loglik_grad(name):
 
 
 def test_golden_c1_tutorial_config_illconditioned():
-    """C1 (tutorial: RBF, N=100, d=2, noise=False, jitter 1e-6) has cond(K) ~ 6e9; the reference formula is
-    only defined to ~cond*eps there, so parity is asserted at that floor."""
+    """C1 (tutorial: RBF, N=100, d=2, noise=False, jitter 1e-6) has cond(K) ~ 6e9: the oracle's own float64 result is
+    off the 50-digit truth (tests/golden/gp_truth_c1.npz, same inputs, hyperparameter row 0) by 2.7e-10 (ll) and 1.3e-6
+    (gradient).  Device and oracle can therefore differ by the sum of their errors; the device's own error is bounded by
+    twice the oracle's in test_gpu_bench_parity.py::test_c1_against_extended_precision_truth, which gives 3x here."""
     g = np.load(os.path.join(HERE, 'golden', 'gp_oracle_rbf_c1.npz'))
+    tr = np.load(os.path.join(HERE, 'golden', 'gp_truth_c1.npz'))
+    assert np.array_equal(tr['thetas'][0], g['theta']) and np.array_equal(tr['X'], g['X'])
     spec = mg.gp_cases()['rbf_c1']['spec']
     eng = engine(spec)
     eng.set_data(g['X'], g['y'])
     ll, grad, info = eng.loglik_grad(g['theta'][None, :])
     th = go.unpack(spec, g['theta'])
-    K = go.cov_matrix(spec, th, g['X']) + spec.jitter * np.eye(100)
-    floor = np.linalg.cond(K) * EPS
+    floor_ll = abs(float(g['ll']) - tr['ll'][0]) / abs(tr['ll'][0])
+    floor_g = grad_err(g['grad'], tr['grad'][0])
+    floor_mu = np.max(np.abs(g['mu'] - tr['mu'][0])) / np.max(np.abs(tr['mu'][0]))
     assert int(info[0]) == 0
-    assert abs(float(ll[0]) - float(g['ll'])) <= max(1e-9, floor) * abs(float(g['ll']))
-    assert grad_err(grad[0].cpu().numpy(), g['grad']) <= 10 * floor
+    assert abs(float(ll[0]) - float(g['ll'])) <= 3 * floor_ll * abs(float(g['ll']))
+    assert grad_err(grad[0].cpu().numpy(), g['grad']) <= 3 * floor_g
     eng.factorize(g['theta'])
     mu, var = eng.predict(g['Xs'])
-    assert np.max(np.abs(mu.cpu().numpy() - g['mu'])) <= 1e-8 * np.max(np.abs(g['mu'])) + 10 * floor
+    assert np.max(np.abs(mu.cpu().numpy() - g['mu'])) <= max(1e-8, 3 * floor_mu) * np.max(np.abs(g['mu']))
     kv = go.kdiag_total(spec, th['kv'])
     assert np.max(np.abs(var.cpu().numpy() - g['var']) / np.maximum(np.abs(g['var']), kv)) <= 1e-8
 

@@ -331,7 +331,7 @@ def test_gpmcmc_pickles_without_device_state(tmp_path):
     g.change_yconrevs([meanstd(g.y[:, 0])])
     g.hypers = {'gv': np.array(1e-4), 'l': np.array([1.0, 2.0]), 'kv': np.array([1.5])}
     g.gp = object()                 # stands for a GPEngine (ctypes handle + device tensors: not picklable state)
-    g._pred_cache = ((1e-6, 12), g.gp, None)
+    g._pred_cache = dict(jitter=1e-6, theta=None, n=12, sum=None, eng=g.gp)
     f = str(tmp_path / 'g.pickle')
     save_object(g, f)
     h = load_object(f)

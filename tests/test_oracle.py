@@ -258,3 +258,53 @@ def test_oracle_gh_stats_grad_vs_finite_differences():
             b = go.gh_stats(mu - h * dmu[:, k], var - h * dvar[:, k], w.rev, mean_add=madd - h * dmadd[:, k], **kw)
             assert np.allclose((a[0] - b[0])[:, 0] / (2 * h), dm[:, k], rtol=1e-6, atol=1e-7 * np.max(np.abs(dm))), kw
             assert np.allclose((a[1] - b[1])[:, 0] / (2 * h), dv[:, k], rtol=1e-6, atol=1e-7 * np.max(np.abs(dv))), kw
+
+
+def test_oracle_against_extended_precision_truth():
+    """oracle/gp_truth.py evaluates the same formulas in 50-digit arithmetic (fixtures: tests/golden/make_truth.py).  An
+    independent pin of the oracle's algebra (kernels, likelihood, analytic gradient, conditional) and the measurement of
+    its float64 noise floor: 1e-12 or better at ordinary conditioning; on the tutorial case (cond(K) ~ 6e9) the oracle
+    itself is only good to ~5e-10 (ll) / ~1e-6 (gradient) -- the floor the C1 device test is held to."""
+    g = np.load(os.path.join(HERE, 'golden', 'gp_truth_m52.npz'))
+    spec = mg.gp_cases()['m52_noise']['spec']
+    for b, t in enumerate(g['thetas']):
+        r = go.loglik(spec, t, g['X'], g['y'])
+        assert abs(r.ll - g['ll'][b]) <= 1e-12 * abs(g['ll'][b])
+        assert np.max(np.abs(r.grad - g['grad'][b]) / np.maximum(np.abs(g['grad'][b]), 1e-3 * np.max(np.abs(g['grad'][b])))) <= 1e-11
+    mu, var = go.predict(spec, g['thetas'][0], g['X'], g['y'], g['Xs'])
+    assert np.max(np.abs(mu - g['mu'][0])) <= 1e-12 * np.max(np.abs(g['mu'][0]))
+    assert np.max(np.abs(var - g['var'][0])) <= 1e-12 * g['thetas'][0][-1]
+    c1 = np.load(os.path.join(HERE, 'golden', 'gp_truth_c1.npz'))
+    spec1 = mg.gp_cases()['rbf_c1']['spec']
+    e_ll = e_g = 0.0
+    for b, t in enumerate(c1['thetas']):
+        r = go.loglik(spec1, t, c1['X'], c1['y'])
+        e_ll = max(e_ll, abs(r.ll - c1['ll'][b]) / abs(c1['ll'][b]))
+        e_g = max(e_g, np.max(np.abs(r.grad - c1['grad'][b]) / np.maximum(np.abs(c1['grad'][b]), 1e-3 * np.max(np.abs(c1['grad'][b])))))
+    assert 1e-12 < e_ll < 5e-9 and 1e-10 < e_g < 1e-5, (e_ll, e_g)     # the floor is real, and no worse than recorded
+
+
+def test_truth_module_reproduces_its_fixture():
+    """the committed truth fixture is what oracle/gp_truth.py produces (one hyperparameter vector, a few seconds)."""
+    from oracle import gp_truth
+    g = np.load(os.path.join(HERE, 'golden', 'gp_truth_m52.npz'))
+    r = gp_truth.evaluate('Matern52', True, 1e-6, g['thetas'][1], g['X'], g['y'])
+    assert r['ll'] == g['ll'][1] and np.array_equal(r['grad'], g['grad'][1])
+
+
+def test_bench_golden_fixtures_are_the_oracle_on_the_bench_inputs():
+    """drift guard for tests/golden/bench_*.npz: the benchmark's workload generators reproduce the inputs the fixtures
+    were made from, and the oracle reproduces a row of each (c3 in full, c2 without the gradient: seconds)."""
+    import zlib
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    for name, B, seed in (('c2', 64, 202), ('c3', 512, 303)):
+        g = np.load(os.path.join(HERE, 'golden', f'bench_{name}.npz'))
+        kw, X, y, th = getattr(bench, f'workload_{name}')()
+        assert [zlib.crc32(np.ascontiguousarray(X).view(np.uint8)), zlib.crc32(np.ascontiguousarray(y).view(np.uint8))] == list(g['data_sum'])
+        thetas = bench.theta_cloud(th, B, seed=seed)
+        assert np.array_equal(thetas[g['rows']], g['thetas'])
+        r = go.loglik(bench.oracle_spec(name), g['thetas'][2], X, y, want_grad=(name == 'c3'))
+        assert abs(r.ll - g['ll'][2]) <= 1e-12 * abs(g['ll'][2])
+        if name == 'c3':
+            assert np.allclose(r.grad, g['grad'][2], rtol=1e-10, atol=1e-10 * np.max(np.abs(r.grad)))

@@ -1,8 +1,9 @@
 """C2 (BASELINE.json configs[1]) through the public API: N=2000, d=8 ARD Matern-5/2 GP with learnable input
 (uniform, kumaraswamy) and output (logarithm, sal, meanstd) warps, MAP fit by L-BFGS-B on the device's likelihood
 gradients -- `GPMCMC.fit(iwgp=True, cwgp=True)` once from the default start (one evaluation per optimiser step, the
-reference's own usage) and once with `restarts=16` (16 optimisers advanced in lock-step, one batched call per round).
-Prints one JSON line.    python tools/c2_map_fit.py"""
+reference's own usage, gpmcmc.py:326-346) and once with `restarts=16` (16 optimisers advanced in lock-step, one batched
+call per round).  With cpu=True the oracle is timed on the host cores on a few of the fit's own evaluations and the CPU
+time of the same fit is extrapolated from the evaluation count.    python tools/c2_map_fit.py [--cpu]"""
 import json
 import os
 import sys
@@ -10,7 +11,6 @@ import time
 
 import numpy as np
 import scipy.stats as st
-import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,49 +18,83 @@ import bench  # noqa: E402
 from andvaranaut_b200 import GPMCMC, wgp  # noqa: E402
 from andvaranaut_b200 import drivers  # noqa: E402
 
-_, X, y, _ = bench.workload_c2()
-d = X.shape[1]
-priors = [st.uniform(0, 1)] * d
+
+def run(cpu=False):
+    import torch
+    kw, X, y, th = bench.workload_c2()
+    N, d = X.shape
+    priors = [st.uniform(0, 1)] * d
+
+    def build():
+        g = GPMCMC(kernel='Matern52', noise=True, nx=d, ny=1, priors=priors, target=lambda x: np.zeros(1), verbose=False,
+                   xconrevs=[wgp(['uniform', 'kumaraswamy'], [1.0, 1.0], xdist=priors[i]) for i in range(d)],
+                   yconrevs=[wgp(['logarithm', 'sal', 'meanstd'], [0.0, 1.0, 0.0, 1.0], y=y)])
+        g.set_data(X, y[:, None])
+        return g
+
+    out = {'metric': 'gp_loglik_grad_evals_per_s', 'unit': 'evals/s', 'scaling': 'replicas only',
+           'workload': 'c2 as the reference runs it: GPMCMC.fit(iwgp=True, cwgp=True), ONE L-BFGS-B chain, one '
+                       'evaluation per optimiser step (B=1), N=2000 d=8 Matern52, P=30'}
+    g = build()
+    g.fit(iwgp=True, cwgp=True, maxeval=3)            # warm-up: library load, allocations
+    g = build()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    data = g.fit(iwgp=True, cwgp=True, return_data=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out.update(value=data['evals'] / dt, seconds=dt, evals=int(data['evals']), logp=float(data['logp']),
+               ms_per_eval=1e3 * dt / data['evals'])
+    pred = g.predict(X[:200])[:, 0]
+    out['train_rmse'] = float(np.sqrt(np.mean((pred - y[:200]) ** 2)))
+    # device time of one B=1 evaluation (CUDA events) and its share of the FP64 rate
+    from andvaranaut_b200.gp import GPEngine
+    eng = GPEngine(**kw, device=g.device)
+    eng.set_data(X, y)
+    tdev = torch.as_tensor(th[None, :], device=eng.device)
+    for _ in range(3):
+        eng.loglik_grad(tdev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        eng.loglik_grad(tdev)
+    e1.record()
+    e1.synchronize()
+    out['device_ms_per_eval_b1'] = e0.elapsed_time(e1) / 20
+    out['device_tflops_b1'] = bench.flops_ll(N, d) / (out['device_ms_per_eval_b1'] * 1e-3) / 1e12
+    out['api_tflops'] = bench.flops_ll(N, d) * out['value'] / 1e12
+    del eng
+    # 16 restarts in lock-step: one batched call per round
+    g2 = build()
+    n0 = [0]
+    orig = drivers.Posterior.logp_dlogp
+
+    def counted(self, z, jacobian):
+        n0[0] += np.atleast_2d(z).shape[0]
+        return orig(self, z, jacobian)
+    drivers.Posterior.logp_dlogp = counted
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        data2 = g2.fit(iwgp=True, cwgp=True, restarts=16, seed=1, return_data=True)
+        torch.cuda.synchronize()
+        dt2 = time.perf_counter() - t0
+    finally:
+        drivers.Posterior.logp_dlogp = orig
+    out['restarts16'] = {'seconds': dt2, 'evals': n0[0], 'evals_per_s': n0[0] / dt2,
+                         'best_logp': float(np.nanmax(data2['logp']))}
+    if cpu:
+        from oracle import gp_oracle as go
+        bench.use_all_host_threads()
+        cores, api = bench.blas_threads()
+        spec = bench.oracle_spec('c2')
+        thetas = bench.theta_cloud(th, 8, seed=202)
+        v, n, dtc = bench.cpu_baseline_ll(spec, X, y, thetas, budget_s=6.0, max_evals=8)
+        out['cpu_baseline'] = {'value': v, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'blas': api,
+                               'sample': f'{n} oracle loglik+grad evaluations of the same model ({dtc:.1f} s)',
+                               'same_fit_seconds_extrapolated': data['evals'] / v}
+    return out
 
 
-def build():
-    g = GPMCMC(kernel='Matern52', noise=True, nx=d, ny=1, priors=priors, target=lambda x: np.zeros(1), verbose=False,
-               xconrevs=[wgp(['uniform', 'kumaraswamy'], [1.0, 1.0], xdist=priors[i]) for i in range(d)],
-               yconrevs=[wgp(['logarithm', 'sal', 'meanstd'], [0.0, 1.0, 0.0, 1.0], y=y)])
-    g.set_data(X, y[:, None])
-    return g
-
-
-out = {'workload': 'c2 MAP fit through GPMCMC.fit(iwgp=True, cwgp=True): N=2000 d=8 Matern52, P=30'}
-g = build()
-g.fit(iwgp=True, cwgp=True, maxeval=3)            # warm-up: library load, allocations
-g = build()
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-data = g.fit(iwgp=True, cwgp=True, return_data=True)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-out['single'] = {'seconds': dt, 'evals': data['evals'], 'logp': data['logp'], 'evals_per_s': data['evals'] / dt,
-                 'l': np.round(g.hypers['l'], 4).tolist(), 'gv': float(g.hypers['gv'])}
-xq = X[:200]
-pred = g.predict(xq)[:, 0]
-out['single']['train_rmse'] = float(np.sqrt(np.mean((pred - y[:200]) ** 2)))
-g2 = build()
-n0 = [0]
-orig = drivers.Posterior.logp_dlogp
-
-
-def counted(self, z, jacobian):
-    n0[0] += np.atleast_2d(z).shape[0]
-    return orig(self, z, jacobian)
-
-
-drivers.Posterior.logp_dlogp = counted
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-data2 = g2.fit(iwgp=True, cwgp=True, restarts=16, seed=1, return_data=True)
-torch.cuda.synchronize()
-dt2 = time.perf_counter() - t0
-out['restarts16'] = {'seconds': dt2, 'evals': n0[0], 'evals_per_s': n0[0] / dt2,
-                     'best_logp': float(np.nanmax(data2['logp'])), 'logp_spread': [float(np.nanmin(data2['logp'])), float(np.nanmax(data2['logp']))]}
-print(json.dumps(out))
+if __name__ == '__main__':
+    print(json.dumps(run(cpu='--cpu' in sys.argv)))
