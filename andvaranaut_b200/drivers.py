@@ -7,10 +7,11 @@ but evaluated for MANY hyperparameter vectors per device call:
                         ``maxeval``, non-finite values mapped to a large penalty);
   * ``find_map_multi``  several independent L-BFGS-B runs (restarts) advanced in lock-step so every round of
                         objective evaluations is ONE batched call;
-  * ``sample``          B chains of Hamiltonian Monte Carlo advanced in lock-step (one batched call per leapfrog
-                        step), dual-averaging step size and diagonal mass adaptation during tuning.  The
-                        reference uses PyMC's NUTS with one process per chain; a lock-step NUTS is a "next" row
-                         -- the sampled density (logp WITH Jacobian) is identical.
+  * ``sample``          B chains of multinomial NUTS (what ``pm.sample`` runs, one process per chain there) advanced
+                        together: every round is one leapfrog step of every chain = one batched call, and chains
+                        move on to their next transition independently (continuous batching, SURVEY 8f.1);
+                        per-chain dual-averaging step size and windowed diagonal mass adaptation during tuning.
+                        The sampled density (logp WITH Jacobian) is the reference's.
 """
 import threading
 
@@ -237,94 +238,113 @@ def _hmc_transition(post, rng, z, lp, g, eps, inv_mass, nleap):
     return z, lp, g, acc, np.full(chains, nleap), np.zeros(chains, dtype=bool)
 
 
-def _nuts_transition(post, rng, z, lp, g, eps, inv_mass, max_treedepth, max_energy_error=1000.0):
-    """One No-U-Turn transition for every chain, the chains advanced in LOCK-STEP: each round of the loop below is one
-    leapfrog step of every chain that is still growing its trajectory = one batched logp/dlogp call.
+class _NutsChains:
+    """Multinomial NUTS for C chains whose transitions run ASYNCHRONOUSLY: every call of :meth:`step` is one leapfrog
+    step of every chain that is inside a transition = one batched logp/dlogp call, and a chain whose tree has ended can
+    start its next transition in the very next round instead of idling until the slowest tree of the batch is done
+    (continuous batching; with lock-step transitions only ~35 % of the chain slots of a device call did work).
 
-    Multinomial NUTS as PyMC and Stan run it (the sampler behind ``pm.sample``, gpmcmc.py:351): the trajectory is
-    doubled in a random direction until the generalised U-turn criterion fires, a leaf diverges (energy error above
-    ``max_energy_error``) or ``max_treedepth`` is reached; the new state is drawn by progressive multinomial sampling
-    (uniform inside a subtree, biased towards the new subtree at every doubling).  The recursion is unrolled: a
-    subtree of 2^j leaves is built leaf by leaf and its internal U-turn checks use the O(j) checkpoint scheme
-    (leaf index bit patterns tell which sub-subtrees end at this leaf), so the state per chain is fixed-size and the
-    chains need not be at the same depth."""
-    C, P = z.shape
-    D = max_treedepth
-    mom = rng.standard_normal(z.shape) / np.sqrt(inv_mass)
-    h0 = -lp + 0.5 * np.sum(mom * mom * inv_mass, axis=1)
-    # main tree: both ends, proposal, log weight (energies relative to h0), momentum sum
-    zl, pl, gl = z.copy(), mom.copy(), g.copy()
-    zr, pr, gr = z.copy(), mom.copy(), g.copy()
-    zp, lpp, gp = z.copy(), lp.copy(), g.copy()
-    logw = np.zeros(C)
-    psum = mom.copy()
-    depth = np.zeros(C, dtype=np.int64)
-    sum_acc = np.zeros(C)
-    nprop = np.zeros(C, dtype=np.int64)
-    diverged = np.zeros(C, dtype=bool)
-    active = np.ones(C, dtype=bool)
-    # subtree under construction
-    going_right = rng.uniform(size=C) < 0.5
-    s_n = np.zeros(C, dtype=np.int64)               # leaves so far
-    s_z, s_p, s_g = z.copy(), mom.copy(), g.copy()  # its growing edge (starts at the main tree's end)
-    s_zp, s_lpp, s_gp = z.copy(), lp.copy(), g.copy()
-    s_logw = np.full(C, -np.inf)
-    s_psum = np.zeros((C, P))
-    s_turn = np.zeros(C, dtype=bool)
-    s_div = np.zeros(C, dtype=bool)
-    s_pfirst = np.zeros((C, P))
-    ck_p = np.zeros((C, D + 1, P))
-    ck_ps = np.zeros((C, D + 1, P))
+    The sampler is the one PyMC and Stan run (``pm.sample``, gpmcmc.py:351): the trajectory is doubled in a random
+    direction until the generalised U-turn criterion fires, a leaf diverges (energy error above ``max_energy_error``)
+    or ``max_treedepth`` is reached; the new state is drawn by progressive multinomial sampling (uniform inside a
+    subtree, biased towards the new subtree at every doubling).  The recursion is unrolled: a subtree of 2^j leaves is
+    built leaf by leaf and its internal U-turn checks use the O(j) checkpoint scheme (leaf index bit patterns tell which
+    sub-subtrees end at this leaf), so the state per chain is fixed-size and chains need not be at the same depth --
+    nor, now, in the same transition."""
 
-    def start_subtree(m):
-        going_right[m] = rng.uniform(size=int(m.sum())) < 0.5
-        right = m & going_right
-        left = m & ~going_right
-        s_z[right], s_p[right], s_g[right] = zr[right], pr[right], gr[right]
-        s_z[left], s_p[left], s_g[left] = zl[left], pl[left], gl[left]
-        s_n[m] = 0
-        s_logw[m] = -np.inf
-        s_psum[m] = 0.0
-        s_turn[m] = False
-        s_div[m] = False
+    def __init__(self, post, rng, C, P, max_treedepth, max_energy_error=1000.0):
+        self.post, self.rng, self.C, self.P = post, rng, C, P
+        self.D, self.max_dE = max_treedepth, max_energy_error
+        D = max_treedepth
+        f = lambda *sh: np.zeros(sh)   # noqa: E731
+        self.eps, self.inv_mass = f(C), np.ones((C, P))
+        self.h0 = f(C)
+        # main tree: both ends, proposal, log weight (energies relative to h0), momentum sum
+        self.zl, self.pl, self.gl = f(C, P), f(C, P), f(C, P)
+        self.zr, self.pr, self.gr = f(C, P), f(C, P), f(C, P)
+        self.zp, self.lpp, self.gp = f(C, P), f(C), f(C, P)
+        self.logw, self.psum = f(C), f(C, P)
+        self.depth = np.zeros(C, dtype=np.int64)
+        self.sum_acc = f(C)
+        self.nprop = np.zeros(C, dtype=np.int64)
+        self.diverged = np.zeros(C, dtype=bool)
+        # subtree under construction
+        self.going_right = np.zeros(C, dtype=bool)
+        self.s_n = np.zeros(C, dtype=np.int64)               # leaves so far
+        self.s_z, self.s_p, self.s_g = f(C, P), f(C, P), f(C, P)   # its growing edge (starts at the main tree's end)
+        self.s_zp, self.s_lpp, self.s_gp = f(C, P), f(C), f(C, P)
+        self.s_logw = np.full(C, -np.inf)
+        self.s_psum = f(C, P)
+        self.s_turn = np.zeros(C, dtype=bool)
+        self.s_div = np.zeros(C, dtype=bool)
+        self.ck_p = f(C, D + 1, P)
+        self.ck_ps = f(C, D + 1, P)
 
-    start_subtree(active.copy())
-    while active.any():
-        a = np.where(active)[0]
-        v = np.where(going_right[a], 1.0, -1.0)[:, None] * eps[a, None]
-        ph = s_p[a] + 0.5 * v * s_g[a]
-        zn = s_z[a] + v * inv_mass[a] * ph
-        lpn, gn, _ = post.logp_dlogp(zn, True)
+    def begin(self, c, z, lp, g, eps, inv_mass):
+        """start a transition of the chains with indices ``c`` from their current states (rows of z, lp, g)."""
+        m = self.rng.standard_normal((len(c), self.P)) / np.sqrt(inv_mass)
+        self.eps[c], self.inv_mass[c] = eps, inv_mass
+        self.h0[c] = -lp + 0.5 * np.sum(m * m * inv_mass, axis=1)
+        self.zl[c], self.pl[c], self.gl[c] = z, m, g
+        self.zr[c], self.pr[c], self.gr[c] = z, m, g
+        self.zp[c], self.lpp[c], self.gp[c] = z, lp, g
+        self.logw[c] = 0.0
+        self.psum[c] = m
+        self.depth[c] = 0
+        self.sum_acc[c] = 0.0
+        self.nprop[c] = 0
+        self.diverged[c] = False
+        self._start_subtree(c)
+
+    def _start_subtree(self, c):
+        gr = self.rng.uniform(size=len(c)) < 0.5
+        self.going_right[c] = gr
+        r, l = c[gr], c[~gr]
+        self.s_z[r], self.s_p[r], self.s_g[r] = self.zr[r], self.pr[r], self.gr[r]
+        self.s_z[l], self.s_p[l], self.s_g[l] = self.zl[l], self.pl[l], self.gl[l]
+        self.s_n[c] = 0
+        self.s_logw[c] = -np.inf
+        self.s_psum[c] = 0.0
+        self.s_turn[c] = False
+        self.s_div[c] = False
+
+    def step(self, a):
+        """one leapfrog step of the chains ``a`` (index array, all inside a transition): ONE batched device call.
+        Returns the indices of the chains whose transition ended with this step; their results are read with
+        :meth:`result`."""
+        rng, inv_mass = self.rng, self.inv_mass
+        v = np.where(self.going_right[a], 1.0, -1.0)[:, None] * self.eps[a, None]
+        ph = self.s_p[a] + 0.5 * v * self.s_g[a]
+        zn = self.s_z[a] + v * inv_mass[a] * ph
+        lpn, gn, _ = self.post.logp_dlogp(zn, True)
         pn = ph + 0.5 * v * gn
         with np.errstate(all='ignore'):
             h1 = -lpn + 0.5 * np.sum(pn * pn * inv_mass[a], axis=1)
-            dE = h1 - h0[a]
+            dE = h1 - self.h0[a]
         dE = np.where(np.isfinite(dE), dE, np.inf)
         leaf_w = -dE
-        div = dE > max_energy_error
+        div = dE > self.max_dE
         with np.errstate(over='ignore'):
-            sum_acc[a] += np.minimum(1.0, np.exp(-dE))
-        nprop[a] += 1
-        s_z[a], s_p[a], s_g[a] = zn, pn, gn
-        first = s_n[a] == 0
-        s_pfirst[a[first]] = pn[first]
+            self.sum_acc[a] += np.minimum(1.0, np.exp(-dE))
+        self.nprop[a] += 1
+        self.s_z[a], self.s_p[a], self.s_g[a] = zn, pn, gn
         # uniform progressive sampling inside the subtree
         with np.errstate(all='ignore'):
-            neww = np.logaddexp(s_logw[a], leaf_w)
+            neww = np.logaddexp(self.s_logw[a], leaf_w)
             take = np.log(rng.uniform(size=len(a))) < leaf_w - neww
         take &= ~div
         ta = a[take]
-        s_zp[ta], s_lpp[ta], s_gp[ta] = zn[take], lpn[take], gn[take]
-        s_logw[a] = neww
-        s_psum[a] += np.where(div[:, None], 0.0, pn)
-        s_div[a] |= div
+        self.s_zp[ta], self.s_lpp[ta], self.s_gp[ta] = zn[take], lpn[take], gn[take]
+        self.s_logw[a] = neww
+        self.s_psum[a] += np.where(div[:, None], 0.0, pn)
+        self.s_div[a] |= div
         # U-turn checks of the sub-subtrees that end at this leaf
-        n = s_n[a]
+        n = self.s_n[a]
         idx_max = _popcount(n >> 1)
         even = (n & 1) == 0
         ea = a[even]
-        ck_p[ea, idx_max[even]] = pn[even]
-        ck_ps[ea, idx_max[even]] = s_psum[ea]
+        self.ck_p[ea, idx_max[even]] = pn[even]
+        self.ck_ps[ea, idx_max[even]] = self.s_psum[ea]
         odd = ~even & ~div
         if odd.any():
             oa = a[odd]
@@ -336,41 +356,59 @@ def _nuts_transition(post, rng, z, lp, g, eps, inv_mass, max_treedepth, max_ener
                 if not m.any():
                     continue
                 om = oa[m]
-                sub = s_psum[om] - ck_ps[om, k] + ck_p[om, k]
-                turn[m] = _turning(inv_mass[om], ck_p[om, k], pn[odd][m], sub)
-            s_turn[oa] |= turn
-        s_n[a] += 1
+                sub = self.s_psum[om] - self.ck_ps[om, k] + self.ck_p[om, k]
+                turn[m] = _turning(inv_mass[om], self.ck_p[om, k], pn[odd][m], sub)
+            self.s_turn[oa] |= turn
+        self.s_n[a] += 1
         # finished subtrees are merged into the main tree
-        done = (s_n[a] == (1 << depth[a])) | s_turn[a] | s_div[a]
+        done = (self.s_n[a] == (1 << self.depth[a])) | self.s_turn[a] | self.s_div[a]
         if not done.any():
-            continue
+            return a[:0]
         da = a[done]
-        ok = ~(s_turn[da] | s_div[da])
+        ok = ~(self.s_turn[da] | self.s_div[da])
         with np.errstate(all='ignore'):
-            tp = np.where(ok, np.exp(np.minimum(0.0, s_logw[da] - logw[da])), 0.0)
+            tp = np.where(ok, np.exp(np.minimum(0.0, self.s_logw[da] - self.logw[da])), 0.0)
         mv = da[rng.uniform(size=len(da)) < tp]
-        zp[mv], lpp[mv], gp[mv] = s_zp[mv], s_lpp[mv], s_gp[mv]
-        r = da[going_right[da]]
-        zr[r], pr[r], gr[r] = s_z[r], s_p[r], s_g[r]
-        l = da[~going_right[da]]
-        zl[l], pl[l], gl[l] = s_z[l], s_p[l], s_g[l]
-        psum[da] += s_psum[da]
-        logw[da] = np.logaddexp(logw[da], s_logw[da])
-        depth[da] += 1
-        diverged[da] |= s_div[da]
-        stop = ~ok | _turning(inv_mass[da], pl[da], pr[da], psum[da]) | (depth[da] >= D)
-        active[da[stop]] = False
-        cont = np.zeros(C, dtype=bool)
-        cont[da[~stop]] = True
-        if cont.any():
-            start_subtree(cont)
-    return zp, lpp, gp, sum_acc / np.maximum(nprop, 1), nprop, diverged
+        self.zp[mv], self.lpp[mv], self.gp[mv] = self.s_zp[mv], self.s_lpp[mv], self.s_gp[mv]
+        r = da[self.going_right[da]]
+        self.zr[r], self.pr[r], self.gr[r] = self.s_z[r], self.s_p[r], self.s_g[r]
+        l = da[~self.going_right[da]]
+        self.zl[l], self.pl[l], self.gl[l] = self.s_z[l], self.s_p[l], self.s_g[l]
+        self.psum[da] += self.s_psum[da]
+        self.logw[da] = np.logaddexp(self.logw[da], self.s_logw[da])
+        self.depth[da] += 1
+        self.diverged[da] |= self.s_div[da]
+        stop = ~ok | _turning(inv_mass[da], self.pl[da], self.pr[da], self.psum[da]) | (self.depth[da] >= self.D)
+        cont = da[~stop]
+        if len(cont):
+            self._start_subtree(cont)
+        return da[stop]
+
+    def result(self, c):
+        """(z, lp, g, mean leaf acceptance, leapfrog steps, diverged) of the finished transitions of chains ``c``"""
+        return (self.zp[c].copy(), self.lpp[c].copy(), self.gp[c].copy(), self.sum_acc[c] / np.maximum(self.nprop[c], 1),
+                self.nprop[c].copy(), self.diverged[c].copy())
+
+
+def _nuts_transition(post, rng, z, lp, g, eps, inv_mass, max_treedepth, max_energy_error=1000.0):
+    """One No-U-Turn transition for every chain with the chains advanced in LOCK-STEP (all start together, finished
+    trees wait for the slowest): the building block of :class:`_NutsChains` driven synchronously; ``sample`` itself
+    runs the chains asynchronously."""
+    C, P = z.shape
+    nc = _NutsChains(post, rng, C, P, max_treedepth, max_energy_error)
+    allc = np.arange(C)
+    nc.begin(allc, z, lp, g, eps, inv_mass)
+    active = np.ones(C, dtype=bool)
+    while active.any():
+        active[nc.step(np.where(active)[0])] = False
+    return nc.result(allc)
 
 
 def sample(post, draws=1000, tune=1000, chains=4, seed=None, target_accept=0.8, path_length=None,
            max_leapfrog=64, start_z=None, init_jitter=1.0, progressbar=False, sampler='nuts', max_treedepth=10):
-    """``chains`` Markov chains advanced in lock-step; every leapfrog step is one batched logp/dlogp call.
-    ``sampler='nuts'`` (default, what ``pm.sample`` runs): multinomial NUTS, see :func:`_nuts_transition`;
+    """``chains`` Markov chains advanced together; every leapfrog step is one batched logp/dlogp call.
+    ``sampler='nuts'`` (default, what ``pm.sample`` runs): multinomial NUTS with asynchronous transitions (continuous
+    batching: a finished tree starts its next transition at once), see :class:`_NutsChains`;
     ``sampler='hmc'``: fixed-length trajectories (jittered length, at most ``max_leapfrog`` steps).  Both share PyMC's
     ``jitter+adapt_diag`` start, dual-averaging step-size adaptation towards ``target_accept`` and a windowed
     diagonal mass-matrix estimate during tuning."""
@@ -397,51 +435,83 @@ def sample(post, draws=1000, tune=1000, chains=4, seed=None, target_accept=0.8, 
     hbar = np.zeros(chains)
     log_eps_bar = np.zeros(chains)
     gamma, t0, kappa = 0.05, 10.0, 0.75
-    # running variance for the diagonal mass matrix (Welford), windowed
-    wn = 0
+    # running variance for the diagonal mass matrix (Welford), windowed; every chain keeps its own iteration count
+    wn = np.zeros(chains)
     wmean = np.zeros((chains, P))
     wm2 = np.zeros((chains, P))
-    win_end, win_len = 100, 100
+    win_end = np.full(chains, 100)
+    win_len = np.full(chains, 100)
     total = tune + draws
     out_z = np.empty((chains, draws, P))
     out_lp = np.empty((chains, draws))
     out_acc = np.empty((chains, draws))
     out_n = np.empty((chains, draws), dtype=np.int64)
     out_div = np.zeros((chains, draws), dtype=bool)
-    for it in range(total):
-        tuning = it < tune
-        if sampler == 'nuts':
-            z, lp, g, acc, nst, dv = _nuts_transition(post, rng, z, lp, g, eps, inv_mass, max_treedepth)
-        else:
+    it = np.zeros(chains, dtype=np.int64)        # transitions finished so far, per chain
+
+    def finish(c, zc, lpc, gc, acc, nst, dv):
+        """transition results of the chains ``c`` (index array): adaptation while tuning, else record the draw"""
+        nonlocal eps, inv_mass, mu, hbar, log_eps_bar
+        z[c], lp[c], g[c] = zc, lpc, gc
+        m = it[c] + 1
+        tun = m <= tune
+        ct, mt = c[tun], m[tun].astype(np.float64)
+        if len(ct):
+            hbar[ct] = (1 - 1 / (mt + t0)) * hbar[ct] + (target_accept - acc[tun]) / (mt + t0)
+            log_eps = mu[ct] - np.sqrt(mt) / gamma * hbar[ct]
+            eta = mt ** (-kappa)
+            log_eps_bar[ct] = eta * log_eps + (1 - eta) * log_eps_bar[ct]
+            eps[ct] = np.exp(log_eps)
+            wn[ct] += 1
+            delta = z[ct] - wmean[ct]
+            wmean[ct] += delta / wn[ct, None]
+            wm2[ct] += delta * (z[ct] - wmean[ct])
+            w = (m[tun] == win_end[ct]) & (m[tun] < tune - 50)
+            cw = ct[w]
+            if len(cw):
+                var = wm2[cw] / np.maximum(wn[cw, None] - 1, 1)
+                inv_mass[cw] = (wn[cw, None] / (wn[cw, None] + 5.0)) * var + 1e-3 * (5.0 / (wn[cw, None] + 5.0))   # Stan's regularisation
+                wn[cw], wmean[cw], wm2[cw] = 0, 0.0, 0.0
+                win_len[cw] *= 2
+                win_end[cw] += win_len[cw]
+                mu[cw] = np.log(10 * eps[cw])
+                hbar[cw] = 0.0
+            last = ct[m[tun] == tune]
+            eps[last] = np.exp(log_eps_bar[last])
+        cd = c[~tun]
+        if len(cd):
+            k = m[~tun] - 1 - tune
+            out_z[cd, k], out_lp[cd, k], out_acc[cd, k] = zc[~tun], lpc[~tun], acc[~tun]
+            out_n[cd, k], out_div[cd, k] = nst[~tun], dv[~tun]
+        it[c] += 1
+
+    allc = np.arange(chains)
+    if sampler == 'nuts':
+        # continuous batching: one round = one leapfrog of EVERY chain that still has transitions to do; a chain whose
+        # tree ended starts its next transition in the next round (its adaptation state is its own)
+        nuts = _NutsChains(post, rng, chains, P, max_treedepth)
+        if total > 0:
+            nuts.begin(allc, z, lp, g, eps, inv_mass)
+        running = np.full(chains, total > 0)
+        rounds = 0
+        while running.any():
+            fin = nuts.step(np.where(running)[0])
+            rounds += 1
+            if len(fin):
+                finish(fin, *nuts.result(fin))
+                again = fin[it[fin] < total]
+                running[fin[it[fin] >= total]] = False
+                if len(again):
+                    nuts.begin(again, z[again], lp[again], g[again], eps[again], inv_mass[again])
+            if progressbar and rounds % 200 == 0:
+                print(f'  round {rounds}: transitions done min {it.min()} / mean {it.mean():.0f} of {total}')
+    else:
+        for _ in range(total):
             nleap = int(rng.integers(max(1, max_leapfrog // 4), max_leapfrog + 1)) if path_length is None \
                 else int(np.clip(np.ceil(path_length / np.median(eps)), 1, max_leapfrog))
-            z, lp, g, acc, nst, dv = _hmc_transition(post, rng, z, lp, g, eps, inv_mass, nleap)
-        if tuning:
-            m = it + 1
-            hbar = (1 - 1 / (m + t0)) * hbar + (target_accept - acc) / (m + t0)
-            log_eps = mu - np.sqrt(m) / gamma * hbar
-            eta = m ** (-kappa)
-            log_eps_bar = eta * log_eps + (1 - eta) * log_eps_bar
-            eps = np.exp(log_eps)
-            wn += 1
-            delta = z - wmean
-            wmean += delta / wn
-            wm2 += delta * (z - wmean)
-            if m == win_end and m < tune - 50:
-                var = wm2 / max(wn - 1, 1)
-                inv_mass = (wn / (wn + 5.0)) * var + 1e-3 * (5.0 / (wn + 5.0))   # Stan's regularisation
-                wn, wmean, wm2 = 0, np.zeros((chains, P)), np.zeros((chains, P))
-                win_len *= 2
-                win_end += win_len
-                mu = np.log(10 * eps)
-                hbar = np.zeros(chains)
-            if m == tune:
-                eps = np.exp(log_eps_bar)
-        else:
-            k = it - tune
-            out_z[:, k], out_lp[:, k], out_acc[:, k], out_n[:, k], out_div[:, k] = z, lp, acc, nst, dv
-        if progressbar and (it + 1) % 50 == 0:
-            print(f'  iter {it + 1}/{total}  mean accept {acc.mean():.2f}  eps {np.median(eps):.3g}')
+            finish(allc, *_hmc_transition(post, rng, z, lp, g, eps, inv_mass, nleap))
+            if progressbar and it[0] % 50 == 0:
+                print(f'  iter {it[0]}/{total}  eps {np.median(eps):.3g}')
     # named posterior arrays
     posterior = {}
     theta = sp.theta_from_z(out_z)[0]
