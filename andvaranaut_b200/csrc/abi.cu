@@ -33,6 +33,7 @@ struct avn_gp {
                                       // first call that enqueues work when no device was visible at create time)
   bool dev_ready = false;             // shared-memory opt-ins / occupancy of this handle's kernels done on `device`
   int fac_resident = 0;               // CTAs of the persistent factor kernel that are resident at once on `device`
+  int fac_resident_fused = 0;         // the same with the fused-panel shared-memory footprint (three tiles)
   unsigned max_spins = 1u << 26;      // bound of the factor kernel's flag waits, in polls (avn_gp_set_debug)
   int fault = 0;                      // fault injection for tests (avn_gp_set_debug)
   int max_groups = 1;                 // independent sample groups on internal streams (avn_gp_set_streams)
@@ -41,7 +42,25 @@ struct avn_gp {
   cudaEvent_t ev[2 * AVN_PH_COUNT] = {};
   bool ev_used[AVN_PH_COUNT] = {};
   double acc_ms[AVN_PH_COUNT] = {};
+  // avn_gp_loglik_grad_host: the whole host-to-host evaluation captured once as a CUDA graph and replayed
+  cudaStream_t hstream = nullptr;     // library-owned: stream capture is not allowed on the legacy default stream
+  cudaEvent_t hev = nullptr;          // orders the replay behind the caller's stream
+  cudaGraphExec_t hexec = nullptr;
+  int64_t hlaunches = 0;              // kernel launches inside the captured graph
+  struct HostKey {
+    const void* theta_host; const void* out_host; const void* staging; const void* ws; const void* X; const void* y;
+    int64_t B, N; int want_grad; unsigned max_spins; int fault;
+    bool operator==(const HostKey& o) const {
+      return theta_host == o.theta_host && out_host == o.out_host && staging == o.staging && ws == o.ws && X == o.X &&
+             y == o.y && B == o.B && N == o.N && want_grad == o.want_grad && max_spins == o.max_spins && fault == o.fault;
+    }
+  } hkey = {};
 };
+
+static void host_graph_drop(avn_gp* gp) {
+  if (gp->hexec) cudaGraphExecDestroy(gp->hexec);
+  gp->hexec = nullptr;
+}
 
 // RAII phase marker: records start/stop events when profiling is on
 struct Phase {
@@ -173,6 +192,9 @@ extern "C" void avn_gp_destroy(avn_gp* gp) {
     if (e) cudaEventDestroy(e);
   for (auto& s : gp->gstream)
     if (s) cudaStreamDestroy(s);
+  host_graph_drop(gp);
+  if (gp->hev) cudaEventDestroy(gp->hev);
+  if (gp->hstream) cudaStreamDestroy(gp->hstream);
   delete gp;
 }
 
@@ -251,8 +273,8 @@ static void layout(const avn_gp* gp, int64_t B, avn_ws_layout* L) {
   L->gpart = take(B * ntiles * MAXACC);
   L->gxpart = take(gp->has_xwarp ? B * nb * npad * kd.d : 0);
   L->fpart = take(B * nb * 2);
-  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], then 8 control words per stream group
-  L->fflags = take((2 * B * nb + 8 * 8 + 1) / 2);
+  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], 8 control words per stream group, sflag [B][nb]
+  L->fflags = take((3 * B * nb + 8 * 8 + 1) / 2);
   L->total = off;
 }
 
@@ -266,6 +288,7 @@ static WsPtrs ws_ptrs(const avn_ws_layout& L, void* ws, int64_t B) {
   p.lflag = reinterpret_cast<int32_t*>(base + L.fflags);
   p.tflag = p.lflag + B * L.nb;
   p.ctl = p.tflag + B * L.nb;
+  p.sflag = p.ctl + 64;
   return p;
 }
 
@@ -323,7 +346,7 @@ static int ensure_ready(avn_gp* gp) {
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   if (cov_smem_bytes(kd) > 48 * 1024) chk(opt_in_smem(cov_kernel, cov_smem_bytes(kd)));
-  chk(opt_in_smem(factor_kernel, FAC_SMEM_BYTES));
+  chk(opt_in_smem(factor_kernel, FAC_SMEM_BYTES_FUSED));
   if (kd.nkern == 1) {
     WsPtrs none{};
     int rc = launch_kinv_fast(true, kd.kern[0], gp->has_xwarp, dim3(1), kinv_fast_smem_bytes(kd), nullptr, kd, 0, 0, nullptr, none);
@@ -348,6 +371,10 @@ static int ensure_ready(avn_gp* gp) {
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES);
   if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
   gp->fac_resident = sms * per_sm;
+  int per_sm_f = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES_FUSED);
+  if (e != cudaSuccess || per_sm_f < 1) return fail_cuda("factor occupancy (fused panel)", e);
+  gp->fac_resident_fused = sms * per_sm_f;
   if (const char* env = getenv("AVN_FAC_CTAS_PER_SM")) gp->fac_resident = sms * atoi(env);   // development knob
   gp->dev_ready = true;
   return 0;
@@ -388,12 +415,6 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
   return 0;
 }
 
-// Persistent grid of the factor kernel: as many CTAs as fit on the handle's device at once (3 per SM; counted by
-// ensure_ready), never more than tasks.
-static int factor_grid(const avn_gp* gp, int64_t total_tasks) {
-  return (int)(total_tasks < gp->fac_resident ? total_tasks : gp->fac_resident);
-}
-
 // Cholesky K -> L in place (kl) and T = L^-1 (t): one persistent dataflow launch (factor.cuh).
 // The caller has zeroed W.lflag / W.tflag / W.ctl on this stream.
 static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int64_t npad, bool want_inverse,
@@ -401,13 +422,20 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   const int nb = (int)(npad / TILE);
   const int64_t total = B * nb * nb;
   if (total > 0x7fffffffLL) return fail("run_factor: B * (N/64)^2 exceeds the task counter");
-  const int grid = factor_grid(gp, total);
+  // Few samples: fewer tile tasks per block step (B * nb) than CTAs that fit with the fused-panel footprint -- the run
+  // time is the chain of diagonal tasks, which the fused panel shortens (factor.cuh); more samples: throughput mode.
+  bool fused = B * nb <= gp->fac_resident_fused;
+  if (const char* env = getenv("AVN_FAC_FUSE")) fused = atoi(env) != 0;   // development knob
+  const int resident = fused ? gp->fac_resident_fused : gp->fac_resident;
+  const int grid = (int)(total < resident ? total : resident);
+  const size_t smem = fused ? FAC_SMEM_BYTES_FUSED : FAC_SMEM_BYTES;
   FactorArgs fa;
   fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info; fa.z = W.z; fa.beta = W.beta;
-  fa.lflag = W.lflag; fa.tflag = W.tflag; fa.ctl = W.ctl;
+  fa.lflag = W.lflag; fa.tflag = W.tflag; fa.sflag = W.sflag; fa.ctl = W.ctl;
   fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.n = (int)gp->N; fa.want_inverse = want_inverse ? 1 : 0;
   fa.max_spins = gp->max_spins;
   fa.fault = gp->fault;
+  fa.fuse_panel = fused ? 1 : 0;
   fa.dgap = 0;   // D(.,s+1) right behind P(.,s,s+1): its first s slabs are final already, only the last one waits
   fa.prof = nullptr;
 #ifdef AVN_FACTOR_PROF
@@ -419,7 +447,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
 #endif
   {
     Phase ph(gp, AVN_PH_FACTOR, st);
-    factor_kernel<<<grid, FAC_THREADS, FAC_SMEM_BYTES, st>>>(fa);
+    factor_kernel<<<grid, FAC_THREADS, smem, st>>>(fa);
     LAUNCH_CHECK("factor_kernel");
   }
 #ifdef AVN_FACTOR_PROF
@@ -477,7 +505,7 @@ static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, 
 }
 
 static cudaError_t zero_flags(const WsPtrs& W, int64_t B, int64_t nb, cudaStream_t st) {
-  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(2 * B * nb + 64), st);
+  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(3 * B * nb + 64), st);
 }
 
 extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
@@ -518,6 +546,7 @@ static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& 
   p.fpart += b0 * nb * 2;
   p.lflag += b0 * nb;
   p.tflag += b0 * nb;
+  p.sflag += b0 * nb;
   return p;
 }
 
@@ -668,6 +697,80 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
   return rc;
 }
 
+// ---- host-buffer evaluation (what find_MAP / pm.sample call once per step: NumPy point in, logp + dlogp out) ----------
+extern "C" size_t avn_gp_host_staging_bytes(const avn_gp* gp, int64_t B) {
+  if (!gp || B < 1) return 0;
+  const int64_t P = gp->kd.P;
+  return (size_t)(align_up(B * P * 8, 256) + align_up(B * (P + 2) * 8, 256));
+}
+
+extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int64_t B, double* out_host, int32_t want_grad,
+                                       void* staging_dev, size_t staging_bytes, void* ws_dev, size_t ws_bytes, void* stream) {
+  if (!gp || !theta_host || !out_host || !staging_dev || !ws_dev) return fail("avn_gp_loglik_grad_host: null argument");
+  if (gp->N < 1) return fail("avn_gp_loglik_grad_host: set_data first");
+  if (B < 1 || B > 65535) return fail("avn_gp_loglik_grad_host: B out of range [1,65535]");
+  if (staging_bytes < avn_gp_host_staging_bytes(gp, B)) return fail("avn_gp_loglik_grad_host: staging buffer too small");
+  avn_ws_layout L;
+  layout(gp, B, &L);
+  if (ws_bytes < (size_t)L.total) return fail("avn_gp_loglik_grad_host: workspace too small");
+  ENTER_DEVICE(gp);
+  const int64_t P = gp->kd.P;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (!gp->hstream) {
+    e = cudaStreamCreateWithFlags(&gp->hstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&gp->hev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail_cuda("host-call stream", e);
+  }
+  double* theta_dev = static_cast<double*>(staging_dev);
+  double* packed = reinterpret_cast<double*>(static_cast<char*>(staging_dev) + align_up(B * P * 8, 256));
+  double* ll_dev = packed;
+  double* grad_dev = packed + B;
+  int32_t* info_dev = reinterpret_cast<int32_t*>(packed + B + B * P);
+  const avn_gp::HostKey key = {theta_host, out_host, staging_dev, ws_dev, gp->X, gp->y, B, gp->N, want_grad ? 1 : 0,
+                               gp->max_spins, gp->fault};
+  if (!gp->hexec || !(key == gp->hkey)) {
+    // capture: H2D of the points, flags, the 8-9 launches of the evaluation, D2H of the packed results
+    host_graph_drop(gp);
+    const bool prof = gp->profiling;
+    gp->profiling = false;   // phase events cannot be recorded into a capture
+    e = cudaStreamBeginCapture(gp->hstream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { gp->profiling = prof; return fail_cuda("begin capture", e); }
+    cudaStream_t hs = gp->hstream;
+    gp->launches = 0;
+    WsPtrs W = ws_ptrs(L, ws_dev, B);
+    int rc = 0;
+    e = cudaMemcpyAsync(theta_dev, theta_host, (size_t)(B * P * 8), cudaMemcpyHostToDevice, hs);
+    if (e == cudaSuccess) e = cudaMemsetAsync(info_dev, 0, (size_t)(B * 8), hs);   // whole [B] doubles slot of the int32 info
+    if (e == cudaSuccess) e = zero_flags(W, B, L.nb, hs);
+    if (e == cudaSuccess) rc = loglik_group(gp, theta_dev, B, ll_dev, want_grad ? grad_dev : nullptr, info_dev, W, L, hs);
+    if (e == cudaSuccess && rc == 0)
+      e = cudaMemcpyAsync(out_host, packed, (size_t)(B * (P + 2) * 8), cudaMemcpyDeviceToHost, hs);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(hs, &graph);
+    gp->profiling = prof;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      return fail_cuda("capture", e != cudaSuccess ? e : e2);
+    }
+    e = cudaGraphInstantiate(&gp->hexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { gp->hexec = nullptr; return fail_cuda("graph instantiate", e); }
+    gp->hkey = key;
+    gp->hlaunches = gp->launches;
+  }
+  gp->launches = gp->hlaunches;
+  // replay behind whatever the caller has enqueued on its stream, wait for the results
+  e = cudaEventRecord(gp->hev, st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(gp->hstream, gp->hev, 0);
+  if (e == cudaSuccess) e = cudaGraphLaunch(gp->hexec, gp->hstream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(gp->hstream);
+  if (e != cudaSuccess) return fail_cuda("graph launch", e);
+  return 0;
+}
+
 // ---- predict -------------------------------------------------------------------------------------
 struct StateLayout {
   int64_t hyp, alpha, xs, x2, t, total;  // byte offsets
@@ -750,6 +853,27 @@ extern "C" int avn_gp_factorize(avn_gp* gp, const double* theta_dev, void* state
   return 0;
 }
 
+// cross-covariance panel + latent mean: single-kernel models take the register-blocked instantiation of their kind
+static void launch_kxs(const KernDesc& kd, dim3 grid, cudaStream_t st, int N, int npad, const HypS* hyp, const double* xs,
+                       const double* x2, const double* alpha, const double* Xs_dev, int64_t M, int64_t m0, int cols,
+                       double* Kxs, double* out_mean_dev, int ns, double* mu_part) {
+  if (kd.nkern == 1) {
+    const size_t smem = kxs1_smem_doubles(kd.d) * 8;
+#define AVN_KXS1(K) \
+  case K: kxs1_kernel<K><<<grid, 256, smem, st>>>(kd, N, npad, hyp, xs, x2, alpha, Xs_dev, M, m0, cols, Kxs, out_mean_dev, ns, mu_part); return;
+    switch (kd.kern[0]) {
+      AVN_KXS1(AVN_RBF)
+      AVN_KXS1(AVN_MATERN52)
+      AVN_KXS1(AVN_MATERN32)
+      AVN_KXS1(AVN_EXPONENTIAL)
+      AVN_KXS1(AVN_RATQUAD)
+    }
+#undef AVN_KXS1
+  }
+  kxs_kernel<<<grid, 256, kxs_smem_bytes(kd), st>>>(kd, N, npad, hyp, xs, x2, alpha, Xs_dev, M, m0, cols, Kxs, out_mean_dev,
+                                                     ns, mu_part);
+}
+
 static const int64_t kPanelCols = 148 * 64 * 2;  // test points per K_xs panel
 
 // Small test batches (BO candidates, refine / inverse-problem starts): fewer 64-point column blocks than CTA slots
@@ -797,7 +921,6 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
   const double* x2 = reinterpret_cast<const double*>(sb + S.x2);
   const double* T = reinterpret_cast<const double*>(sb + S.t);
   double* Kxs = static_cast<double*>(ws_dev);
-  const size_t smem_kxs = kxs_smem_bytes(kd);
   for (int64_t m0 = 0; m0 < M; m0 += cols_cap) {
     const int64_t cols = align_up((M - m0) < cols_cap ? (M - m0) : cols_cap, TILE);
     const unsigned nblk = (unsigned)(cols / TILE);
@@ -805,8 +928,8 @@ extern "C" int avn_gp_predict(avn_gp* gp, const void* state_dev, const double* X
     double* vpart = mu_part + (int64_t)ns * cols;  // [ns][cols]
     {
       Phase ph(gp, AVN_PH_KXS, st);
-      kxs_kernel<<<dim3(nblk, ns), 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0,
-                                                        (int)cols, Kxs, out_mean_dev, ns, mu_part);
+      launch_kxs(kd, dim3(nblk, ns), st, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols, Kxs,
+                 out_mean_dev, ns, mu_part);
       LAUNCH_CHECK("kxs_kernel");
     }
     Phase ph2(gp, AVN_PH_PREDICT_VAR, st);
@@ -860,7 +983,6 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
   const double* xs = reinterpret_cast<const double*>(sb + S.xs);
   const double* x2 = reinterpret_cast<const double*>(sb + S.x2);
   const double* T = reinterpret_cast<const double*>(sb + S.t);
-  const size_t smem_kxs = kxs_smem_bytes(kd);
   const size_t smem_pg = predict_grad_smem_bytes(kd);   // opted in by ensure_ready when above 48 KB
   avn_epilogue latent = *epi;
   latent.mode = 0;
@@ -874,8 +996,8 @@ extern "C" int avn_gp_predict_grad(avn_gp* gp, const void* state_dev, const doub
     double* gpart = vpart + (int64_t)ns * cols;    // [ns][cols][2 d]
     {
       Phase ph(gp, AVN_PH_KXS, st);
-      kxs_kernel<<<dim3(nblk, ns), 256, smem_kxs, st>>>(kd, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0,
-                                                        (int)cols, Kxs, out_mean_dev, ns, mu_part);
+      launch_kxs(kd, dim3(nblk, ns), st, (int)gp->N, (int)npad, hyp, xs, x2, alpha, Xs_dev, M, m0, (int)cols, Kxs,
+                 out_mean_dev, ns, mu_part);
       LAUNCH_CHECK("kxs_kernel");
     }
     Phase ph2(gp, AVN_PH_PREDICT_VAR, st);

@@ -40,6 +40,9 @@ constexpr int FAC_LDS = TILE + SPAD;                                 // 68: conf
 constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
 // two staged 64 x 64 tiles for the epilogues alias the pipeline buffers
 constexpr size_t FAC_SMEM_BYTES = cmax((size_t)2 * TILE * FAC_LDS * 8, cmax(FacKK::SMEM_BYTES, FacKR::SMEM_BYTES));
+// fused-panel launches (few samples): a third staged tile behind the first two
+constexpr size_t FAC_SMEM_BYTES_FUSED = (size_t)3 * TILE * FAC_LDS * 8;
+static_assert(FAC_SMEM_BYTES == (size_t)2 * TILE * FAC_LDS * 8, "the third tile must lie behind the pipeline buffers");
 
 #ifdef AVN_FACTOR_PROF
 // timeline of the critical chain (B = 1): thread 0 logs (task type, k, event, globaltimer ns) for the diagonal tasks
@@ -83,6 +86,7 @@ struct FactorArgs {
   int32_t* info;        // [B]              first non-positive pivot (1-based) or 0
   int32_t* lflag;       // [B][nb]
   int32_t* tflag;       // [B][nb]
+  int32_t* sflag;       // [B][nb]  fused-panel launches: 1 = S of the tile (i, i-1) is parked in the T slab
   int32_t* ctl;         // [0] ticket counter, [1] abort flag (a wait exceeded its bound)
   int npad, nb, B;
   int n;                // valid rows (N <= npad): tiles of the last block row skip their padding fragments
@@ -90,6 +94,7 @@ struct FactorArgs {
   int dgap;             // slots between P(.,s,s+1) and the look-ahead D(.,s+1)
   unsigned max_spins;   // bound of every flag wait in polls (avn_gp_set_debug; default 2^26, several seconds)
   int fault;            // fault injection (tests): 1 = the panel task P(0,0,1) never publishes its flag
+  int fuse_panel;       // 1: diagonal tasks form their own panel tile L[k,k-1] (few samples; needs FAC_SMEM_BYTES_FUSED)
   long long* prof;      // AVN_FACTOR_PROF builds: 8 cycle counters (ticket, wait, gemm, wait T_kk, epilogue, diag, -, -)
 };
 
@@ -374,27 +379,48 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
       double x[PB];
 #pragma unroll
       for (int c = 0; c < PB; c++) x[c] = sA[(c0 + i) * FAC_LDS + c0 + c];
-      double pv = x[0];   // lane j: A_jj after the updates of steps < j, formed one step ahead (see below)
       double myinv = 1.0;
       int badj = 0;       // first non-positive pivot of this sub-block (1-based), 0: none
+      // Software-pipelined by hand: the pivot of step j + 1 (lane j+1's own A_jj, complete as soon as that lane has
+      // squared its entry of column j) is broadcast and its rsqrt started BEFORE the rest of column j is exchanged and
+      // applied -- a warp issues in order, so with the exchange first the ~100-cycle shuffle + rsqrt chain of the next
+      // step only began after the exchange's store -> barrier -> load -> FMA sequence (~200 cycles per step instead of
+      // the chain's ~120).
+      double piv = __shfl_sync(0xffffffffu, x[0], 0);
+      bool bad = !(piv > 0.0);   // also catches NaN
+      badj = bad ? 1 : 0;
+      piv = bad ? 1.0 : piv;
+      double inv = rsqrt_nobranch(piv);
 #pragma unroll
       for (int j = 0; j < PB; j++) {
-        double piv = __shfl_sync(0xffffffffu, pv, j);
-        const bool bad = !(piv > 0.0);   // also catches NaN
-        badj = (bad && badj == 0) ? j + 1 : badj;
-        piv = bad ? 1.0 : piv;
-        const double inv = rsqrt_nobranch(piv);
         myinv = (i == j) ? inv : myinv;
         const double li = (i == j) ? piv * inv : x[j] * inv;        // column j of L (rows >= j)
-        // the next pivot needs only lane j+1's own square: formed before any shuffle of this step
-        pv = fma(-li, li, x[(j + 1) & (PB - 1)]);
+        if (j + 1 < PB) {
+          // the next pivot needs only lane j+1's own square
+          const double pv = fma(-li, li, x[j + 1]);
+          piv = __shfl_sync(0xffffffffu, pv, j + 1);
+          bad = !(piv > 0.0);
+          badj = (bad && badj == 0) ? j + 2 : badj;
+          piv = bad ? 1.0 : piv;
+          inv = rsqrt_nobranch(piv);
+          // column j of L reaches the other lanes through 16 doubles of shared memory (one store, then 128-bit broadcast
+          // loads) instead of one 64-bit shuffle per entry: 15 - j shuffles = 2 (15 - j) SHFL at a quarter-rate issue
+          // slot each made the step issue-bound.  Two buffers (the panel's own, still unused slots of dval / sinv)
+          // alternate, so a step's store cannot overtake the previous step's loads.  Same operands, same FMAs as the
+          // shuffle form: bit-identical.
+          double* colbuf = (j & 1) ? sinv + c0 : dval + c0;
+          if (lane < PB) colbuf[i] = li;
+          __syncwarp();
 #pragma unroll
-        for (int c = j + 1; c < PB; c++) {
-          const double lc = __shfl_sync(0xffffffffu, li, c);
-          x[c] = fma(-li, lc, x[c]);                                 // right of the diagonal: never used
+          for (int q = (j + 1) / 2; q < PB / 2; q++) {
+            const double2 lc = reinterpret_cast<const double2*>(colbuf)[q];
+            if (2 * q > j) x[2 * q] = fma(-li, lc.x, x[2 * q]);      // right of the diagonal: never used
+            x[2 * q + 1] = fma(-li, lc.y, x[2 * q + 1]);
+          }
         }
         x[j] = li;
       }
+      __syncwarp();   // the last column loads are done before dval / sinv receive their final values
       DPROF(8);
       if (lane == 0 && badj != 0 && *s_bad == 0) *s_bad = pivot_base + c0 + badj;
       if (lane < PB) {
@@ -486,13 +512,34 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
   DPROF(12);
 }
 
+// X = S T_kk^T on 8 x 8 fragments, S and T_kk staged in shared memory (pitch FAC_LDS).  T_kk is lower triangular: the
+// fragment column jf needs k < 8 jf + 8 only.  Warp w takes the fragment columns w and 7 - w (18 four-deep steps per row
+// fragment between them, the same for every warp) and all eight row fragments: 144 DMMAs per warp, against 128 / 256
+// with the 32 x 32 quadrant layout.  xa[ii][c] = fragment (row ii, column c ? 7 - w : w).
+__device__ __forceinline__ void panel_product(double (&xa)[8][2][2], const double* sS, const double* sTk, int warp, int gq,
+                                              int t) {
+#pragma unroll
+  for (int ii = 0; ii < 8; ii++) xa[ii][0][0] = xa[ii][0][1] = xa[ii][1][0] = xa[ii][1][1] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const int jf = c ? 7 - warp : warp;
+    const int kmax = 8 * jf + 8;
+#pragma unroll 2
+    for (int kk = 0; kk < kmax; kk += 4) {
+      const double bv = sTk[(8 * jf + gq) * FAC_LDS + kk + t];
+#pragma unroll
+      for (int ii = 0; ii < 8; ii++) dmma884(xa[ii][c][0], xa[ii][c][1], sS[(8 * ii + gq) * FAC_LDS + kk + t], bv);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_ticket;
   __shared__ int s_known;
   __shared__ int s_bad;
-  __shared__ double s_dval[TILE];
-  __shared__ double s_inv[TILE];
+  __shared__ __align__(16) double s_dval[TILE];
+  __shared__ __align__(16) double s_inv[TILE];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % 2, wn = warp / 2, gq = lane >> 2, t = lane & 3;
   const int npad = fa.npad, nb = fa.nb, B = fa.B;
@@ -501,13 +548,23 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
   double* sA = smem;
   double* sB = smem + TILE * FAC_LDS;
   FPROF_DECL;
+  // The ticket of the NEXT task is drawn while the current one runs (thread 0 keeps it in a register), so the round
+  // trip of the atomic is off the path between two tasks.  Still deadlock-free: the smallest unfinished ticket is never
+  // one that is merely held -- its holder would be running a smaller, unfinished one -- so it is always running, and
+  // everything it waits on has finished.
+  // Throughput launches only: with few samples the CTAs run far ahead of the chain of diagonal tasks and mostly wait, and
+  // a ticket held behind a waiting task would keep the next link of that chain from starting.
+  const bool prefetch = !fa.fuse_panel;
+  int next_ticket = 0;
+  if (tid == 0 && prefetch) next_ticket = atomicAdd(fa.ctl, 1);
   for (;;) {
     __syncthreads();  // everyone is done with s_ticket and the staged tiles of the previous task
-    if (tid == 0) s_ticket = atomicAdd(fa.ctl, 1);
+    if (tid == 0) s_ticket = prefetch ? next_ticket : atomicAdd(fa.ctl, 1);
     __syncthreads();
     const int ticket = s_ticket;
     FPROF(0);
     if (ticket >= total) break;
+    if (tid == 0 && prefetch) next_ticket = atomicAdd(fa.ctl, 1);
     // ticket -> task (see the header comment for the order)
     int type, k, idx = 0, b;   // type 0: D(b,k)   1: P(b,k,i=idx)   2: R(b,k,j=idx)
     if (ticket < B) {
@@ -542,6 +599,16 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       double* Akk = L + (int64_t)k0 * npad + k0;
       double* Tkk = T + (int64_t)k0 * npad + k0;
       FEVENT(0, k, 0);
+      // Few samples (fa.fuse_panel: fewer tile tasks per step than resident CTAs, the chain of diagonal tasks IS the run
+      // time): this task forms the panel tile L[k,k-1] = S T_mm^T (m = k - 1) itself, in shared memory, from the S that
+      // P(b,m,k) accumulated and parked (sflag), instead of waiting for P(b,m,k) to see T_mm, multiply, store, publish
+      // and then fetching the tile back -- between two diagonal factorisations that is one flag hop, one tile store +
+      // release and one staging round less.  P(b,m,k) still finishes the tile (everybody else reads it from L); the product
+      // is the same code on the same operands, so both modes give the same bits.  The launch then carries a third
+      // 64 x 64 tile of shared memory (2 CTAs per SM).
+      const bool fuse = fa.fuse_panel && k > 0;
+      double* blk = fuse ? smem + 2 * TILE * FAC_LDS : sA;   // the diagonal block: A_kk updated, then L_kk
+      double* tin = fuse ? sA : sB;                          // receives T_kk
       FacKK g;
       load_neg_tile(g.acc, Akk, npad, wm, wn, gq, t);
       if (k > 0) {
@@ -560,35 +627,79 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
+          *reinterpret_cast<double2*>(&blk[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
         }
-      if (k > 0) {
+      if (fuse) {
+        // S = A[k,m] - sum_{c<m} L[k,c] L[m,c]^T was parked by P(b,m,k) in the still unused tile (k,m) of the T slab (R(b,k,m)
+        // writes it only after this task has published T_kk) long before T_mm exists: fetched while D(b,m) factorises ...
+        const int m0 = k0 - TILE;
+        wait_flag(fa.sflag + (int64_t)b * nb + k, 1, fa.ctl, fa.max_spins);
+        stage_tile(sA, T + (int64_t)k0 * npad + m0, npad);
+        // ... then T_mm (the one thing the chain waits for), the product, and X stays in shared memory
+        FEVENT(0, k, 4);
+        wait_flag(lflag + k - 1, k, fa.ctl, fa.max_spins);
+        FEVENT(0, k, 5);
+        stage_tile(sB, T + (int64_t)m0 * npad + m0, npad);
+        __syncthreads();
+        double xa[8][2][2];
+        panel_product(xa, sA, sB, warp, gq, t);
+        __syncthreads();   // everyone has read S and T_mm
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int jf = c ? 7 - warp : warp;
+#pragma unroll
+          for (int ii = 0; ii < 8; ii++)
+            *reinterpret_cast<double2*>(&sB[(8 * ii + gq) * FAC_LDS + 8 * jf + 2 * t]) = make_double2(xa[ii][c][0], xa[ii][c][1]);
+        }
+        __syncthreads();
+        FEVENT(0, k, 6);
+      } else if (k > 0) {
         // ... and block column k-1, what the whole factorisation waits for (published by the panel task of the previous
         // step), is applied there: the 64 x 64 tile L[k,k-1] is fetched in ONE round of loads (sixteen 16-byte loads in
-        // flight per thread, instead of four pipeline slabs issued two at a time) and the update runs on the 36 8 x 8
-        // fragments of the lower triangle only, nine per warp (the 32 x 32 quadrant layout of the pipeline computes 48
-        // fragments on three warps)
+        // flight per thread, instead of four pipeline slabs issued two at a time)
         FEVENT(0, k, 4);
         wait_flag(lflag + k, k, fa.ctl, fa.max_spins);
         FEVENT(0, k, 5);
         stage_tile(sB, L + (int64_t)k0 * npad + (k0 - TILE), npad);
         __syncthreads();
         FEVENT(0, k, 6);
-        for (int q = warp; q < 36; q += FAC_THREADS / 32) {
-          int fi = 0;
-          while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
-          const int fj = q - fi * (fi + 1) / 2;
-          double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      }
+      if (k > 0) {
+        // the update with block column k-1 runs on the 36 8 x 8 fragments of the lower triangle only, nine per warp (the
+        // 32 x 32 quadrant layout of the pipeline computes 48 fragments on three warps);
+        // three fragments in flight per warp (six independent accumulator chains; one fragment at a time left the warp
+        // waiting on an 8-deep dependent DMMA chain: this update is on the critical path of a single factorisation).
+        // Per fragment the order of the DMMAs is unchanged, so the result is bit-identical to the one-at-a-time loop.
+        for (int q0 = warp; q0 < 36; q0 += 3 * (FAC_THREADS / 32)) {
+          const double* pa[3];
+          const double* pb[3];
+          double2* dst[3];
+          double acc[3][4];
 #pragma unroll
-          for (int kk = 0; kk < TILE; kk += 8) {
-            dmma884(acc0, acc1, sB[(8 * fi + gq) * FAC_LDS + kk + t], sB[(8 * fj + gq) * FAC_LDS + kk + t]);
-            dmma884(acc2, acc3, sB[(8 * fi + gq) * FAC_LDS + kk + 4 + t], sB[(8 * fj + gq) * FAC_LDS + kk + 4 + t]);
+          for (int u = 0; u < 3; u++) {
+            const int q = q0 + u * (FAC_THREADS / 32);   // < 36: nine fragments per warp
+            int fi = 0;
+            while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
+            const int fj = q - fi * (fi + 1) / 2;
+            pa[u] = sB + (8 * fi + gq) * FAC_LDS + t;
+            pb[u] = sB + (8 * fj + gq) * FAC_LDS + t;
+            dst[u] = reinterpret_cast<double2*>(&blk[(8 * fi + gq) * FAC_LDS + 8 * fj + 2 * t]);
+            acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
           }
-          double2* dst = reinterpret_cast<double2*>(&sA[(8 * fi + gq) * FAC_LDS + 8 * fj + 2 * t]);
-          double2 cur = *dst;
-          cur.x -= acc0 + acc2;
-          cur.y -= acc1 + acc3;
-          *dst = cur;
+#pragma unroll
+          for (int kk = 0; kk < TILE; kk += 8)
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+              dmma884(acc[u][0], acc[u][1], pa[u][kk], pb[u][kk]);
+              dmma884(acc[u][2], acc[u][3], pa[u][kk + 4], pb[u][kk + 4]);
+            }
+#pragma unroll
+          for (int u = 0; u < 3; u++) {
+            double2 cur = *dst[u];
+            cur.x -= acc[u][0] + acc[u][2];
+            cur.y -= acc[u][1] + acc[u][3];
+            *dst[u] = cur;
+          }
         }
         FPROF(2);
       }
@@ -596,7 +707,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       if (tid == 0) s_bad = __ldcg(fa.info + b);
       __syncthreads();
       FPROF(7);
-      diag_chol_inv_blocked(sA, sB, s_dval, s_inv, &s_bad, k0, fa.prof);
+      diag_chol_inv_blocked(blk, tin, s_dval, s_inv, &s_bad, k0, fa.prof);
       FPROF(6);
       FEVENT(0, k, 2);
       // beta = T z, diagonal-block share: row r of T_kk times z_k (fixed order; off the flags' path: after the publish)
@@ -604,14 +715,17 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       // read by no task of this kernel and follows behind the flags
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
-        *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sB[r * FAC_LDS + c]);
+        *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&tin[r * FAC_LDS + c]);
       }
       if (tid == 0) fa.info[b] = s_bad;
+      // lflag[k] = k + 1 also says "block row k of L is final up to column k": with the fused panel this task did not wait
+      // for P(b,k-1,k), whose own (smaller) value of the flag must be in place before this one -- it finished long ago
+      if (fuse) wait_flag(lflag + k, k, fa.ctl, fa.max_spins);
       publish2(lflag + k, k + 1, tflag + k, k + 1);
       FEVENT(0, k, 3);
       for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
         const int r = e >> 5, c = (e & 31) * 2;
-        *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&sA[r * FAC_LDS + c]);
+        *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&blk[r * FAC_LDS + c]);
       }
       if (warp == 0) {   // sum of log L_ii in a fixed order
         double v = log(s_dval[lane]) + log(s_dval[lane + 32]);
@@ -621,7 +735,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
         const int r = tid - 64;
         const double* zk = fa.z + (int64_t)b * npad + k0;
         double acc = 0.0;
-        for (int c = 0; c <= r; c++) acc = fma(sB[r * FAC_LDS + c], __ldg(zk + c), acc);
+        for (int c = 0; c <= r; c++) acc = fma(tin[r * FAC_LDS + c], __ldg(zk + c), acc);
         fa.beta[(int64_t)b * npad + k0 + r] = acc;
       }
       FPROF(5);
@@ -645,6 +759,18 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
           *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
         }
+      if (fa.fuse_panel && i == k + 1) {
+        // fused-panel launches: S goes to the unused tile (i,k) of the T slab for D(b,i) (see there)
+        double* Sik = T + (int64_t)i0 * npad + k0;
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+            *reinterpret_cast<double2*>(Sik + (int64_t)r * npad + c) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
+          }
+        publish(fa.sflag + (int64_t)b * nb + i, 1);
+      }
       FPROF(4);
       if (i == k + 1) FEVENT(1, k, 1);
       wait_flag(lflag + k, k + 1, fa.ctl, fa.max_spins);   // T[k,k] is there (also orders the sA writes)
@@ -652,24 +778,10 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
       if (i == k + 1) FEVENT(1, k, 2);
       stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
       __syncthreads();
-      // X = S T_kk^T on 8 x 8 fragments.  T_kk is lower triangular: the fragment column jf needs k < 8 jf + 8 only.  Warp w
-      // takes the fragment columns w and 7 - w (18 four-deep steps per row fragment between them, the same for every
-      // warp) and all eight row fragments: 144 DMMAs per warp, against 128 / 256 with the 32 x 32 quadrant layout.
+      // X = S T_kk^T (panel_product), straight from the accumulators to the tile's place in L
       {
         double xa[8][2][2];
-#pragma unroll
-        for (int ii = 0; ii < 8; ii++) xa[ii][0][0] = xa[ii][0][1] = xa[ii][1][0] = xa[ii][1][1] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const int jf = c ? 7 - warp : warp;
-          const int kmax = 8 * jf + 8;
-#pragma unroll 2
-          for (int kk = 0; kk < kmax; kk += 4) {
-            const double bv = sB[(8 * jf + gq) * FAC_LDS + kk + t];
-#pragma unroll
-            for (int ii = 0; ii < 8; ii++) dmma884(xa[ii][c][0], xa[ii][c][1], sA[(8 * ii + gq) * FAC_LDS + kk + t], bv);
-          }
-        }
+        panel_product(xa, sA, sB, warp, gq, t);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           const int jf = c ? 7 - warp : warp;

@@ -28,6 +28,7 @@ struct WsPtrs {
   double* fpart;   // [B][nb][2]              per block row: beta_k^T beta_k, sum log diag(L_kk)
   int32_t* lflag;  // [B][nb]                 progress flags of the factor kernel (factor.cuh)
   int32_t* tflag;  // [B][nb]
+  int32_t* sflag;  // [B][nb]                 behind ctl
   int32_t* ctl;    // [8]                     ticket counter, abort flag
 };
 
@@ -671,6 +672,122 @@ __global__ void __launch_bounds__(256) kxs_kernel(KernDesc kd, int N, int npad, 
   __syncthreads();
   if (tid < TILE) {
     const double sum = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    if (nsplit > 1) mu_part[(int64_t)blockIdx.y * mld + col0 + tid] = sum;
+    else if (m_begin + col0 + tid < M) mu[m_begin + col0 + tid] = sum;
+  }
+}
+
+// Single-kernel models, kernel kind known at compile time: the cross-covariance panel in 4 x 4 register blocks (the
+// tile and thread mapping of cov1_kernel), training rows staged block by block in shared memory with the next block
+// prefetched into registers, no switch / fold in the element loop.  Same contract as kxs_kernel (grid (nblk, nsplit),
+// 256 threads); the latent mean is summed per thread over its rows in rising order and then over the 16 row groups
+// of the CTA in fixed order.  The one-element-at-a-time kernel above ran at 7 % of the HBM write rate (FP64 pipe
+// 15 % active, latency-bound on its L1 reads); this one is bound by the FP64 pipe (sqrt + exp per element).
+// shared: xt [d][64] test points, x2t [64], xr [d][64] training rows of the current block, x2r [64], al [64],
+//         part [16][64]
+__host__ __device__ inline size_t kxs1_smem_doubles(int d) { return (size_t)(2 * d * TILE + 3 * TILE + 16 * TILE); }
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 2) kxs1_kernel(KernDesc kd, int N, int npad, const HypS* __restrict__ hyp_g,
+                                                      const double* __restrict__ xs_tr, const double* __restrict__ x2_tr,
+                                                      const double* __restrict__ alpha, const double* __restrict__ Xtest,
+                                                      int64_t M, int64_t m_begin, int mld, double* __restrict__ Kxs,
+                                                      double* __restrict__ mu, int nsplit, double* __restrict__ mu_part) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, d = kd.d;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  double* sxt = smem;                  // [d][64]
+  double* s2t = sxt + d * TILE;        // [64]
+  double* sxr = s2t + TILE;            // [d][64]
+  double* s2r = sxr + d * TILE;        // [64]
+  double* sal = s2r + TILE;            // [64]
+  double* part = sal + TILE;           // [16][64]
+  const double kvk = hyp_g->kv[0], kalpha = hyp_g->alpha;
+  if (tid < TILE) {
+    const int64_t mg = m_begin + col0 + tid;
+    double tmp[MAXD];
+    for (int m = 0; m < d; m++) {
+      const double x = (mg < M) ? Xtest[mg * d + m] : 0.0;
+      tmp[m] = __dmul_rn(x, hyp_g->invl[0][m]);
+      sxt[m * TILE + tid] = tmp[m];
+    }
+    s2t[tid] = sumsq_numpy_order(tmp, d);
+  }
+  const int nbk = npad / TILE, per = (nbk + nsplit - 1) / nsplit;
+  const int r0 = min(npad, (int)blockIdx.y * per * TILE), r1 = min(npad, r0 + per * TILE);
+  const int tx = tid & 15, ty = tid >> 4;
+  // register prefetch of one training block: 64 d scaled inputs (<= 4 per thread), 64 row norms, 64 alphas
+  constexpr int PF = (MAXD * TILE + 255) / 256;
+  double pf[PF], pfv = 0.0;
+  auto fetch = [&](int n0) {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int e = tid + 256 * u;
+      pf[u] = (e < TILE * d) ? xs_tr[(int64_t)n0 * d + e] : 0.0;
+    }
+    if (tid < TILE) pfv = x2_tr[n0 + tid];
+    else if (tid < 2 * TILE) pfv = alpha[n0 + tid - TILE];
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      const int e = tid + 256 * u;
+      if (e < TILE * d) {
+        const int r = e / d, m = e - r * d;
+        sxr[m * TILE + r] = pf[u];
+      }
+    }
+    if (tid < TILE) s2r[tid] = pfv;
+    else if (tid < 2 * TILE) sal[tid - TILE] = pfv;
+  };
+  double macc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (r0 < r1) fetch(r0);
+  for (int n0 = r0; n0 < r1; n0 += TILE) {
+    __syncthreads();   // the previous block's shared rows are no longer read (first pass: test points staged)
+    stash();
+    __syncthreads();
+    if (n0 + TILE < r1) fetch(n0 + TILE);
+    double dot[4][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) dot[rr][cc] = 0.0;
+    for (int m = 0; m < d; m++) {
+      const double2* pi = reinterpret_cast<const double2*>(sxr + m * TILE + ty * 4);
+      const double2* pj = reinterpret_cast<const double2*>(sxt + m * TILE + tx * 4);
+      const double2 a0 = pi[0], a1 = pi[1], b0 = pj[0], b1 = pj[1];
+      const double xi[4] = {a0.x, a0.y, a1.x, a1.y}, xj[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) dot[rr][cc] = fma(xi[rr], xj[cc], dot[rr][cc]);   // sequential in m
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+      const int n = n0 + ty * 4 + rr;
+      const double n2 = s2r[ty * 4 + rr], al = sal[ty * 4 + rr];
+      double out[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        double r2 = __dadd_rn(__dmul_rn(-2.0, dot[rr][cc]), __dadd_rn(n2, s2t[tx * 4 + cc]));
+        r2 = r2 > 0.0 ? r2 : 0.0;
+        double kk, dk;
+        kern_val_fast<KIND, false>(r2, kalpha, kk, dk);
+        out[cc] = (n < N) ? __dmul_rn(kvk, kk) : 0.0;
+        macc[cc] = fma(out[cc], al, macc[cc]);
+      }
+      double2* dst = reinterpret_cast<double2*>(Kxs + (int64_t)n * mld + col0 + tx * 4);
+      dst[0] = make_double2(out[0], out[1]);
+      dst[1] = make_double2(out[2], out[3]);
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; cc++) part[ty * TILE + tx * 4 + cc] = macc[cc];
+  __syncthreads();
+  if (tid < TILE) {
+    double sum = 0.0;
+#pragma unroll
+    for (int g = 0; g < 16; g++) sum += part[g * TILE + tid];
     if (nsplit > 1) mu_part[(int64_t)blockIdx.y * mld + col0 + tid] = sum;
     else if (m_begin + col0 + tid < M) mu[m_begin + col0 + tid] = sum;
   }

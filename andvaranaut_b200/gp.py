@@ -207,12 +207,46 @@ class GPEngine:
         self._last_B = B
         return ll, grad, info
 
-    @_on_device
-    def loglik_grad_host(self, theta):
-        """host arrays in, host arrays out: theta [B,P] NumPy -> (ll [B], grad [B,P], info [B]) NumPy.  The three results
-        live in ONE device buffer and come back with one device->host copy (the optimiser / sampler drivers call this
-        once per step, where three separate synchronising copies cost ~0.1 ms of a 1.4 ms evaluation)."""
+    def loglik_grad_host(self, theta, want_grad=True):
+        """host arrays in, host arrays out: theta [B,P] NumPy -> (ll [B], grad [B,P], info [B]) NumPy -- the call the
+        optimiser / sampler drivers make once per step.  From the second consecutive call with the same batch size on
+        it goes through ``avn_gp_loglik_grad_host``: the point is written into a pinned host buffer and the host->device
+        copy, the launches of the evaluation and ONE packed device->host copy of ll, grad and info are a CUDA graph
+        inside the library (captured once, replayed afterwards), so a step costs one C call.  A batch size seen for the
+        first time (the drain of a sampler run, one-off calls) takes the same launches un-captured."""
         theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        B, P = theta.shape
+        if P != self.P:
+            raise ValueError(f'theta must have {self.P} columns')
+        if getattr(self, '_host_last_B', None) != B:
+            self._host_last_B = B
+            return self._loglik_grad_host_plain(theta, want_grad)
+        hc = getattr(self, '_hostcall', None)
+        if hc is None or hc['B'] != B or hc['ws'] is not self._workspace(B):
+            with torch.cuda.device(self.device):
+                th_host = torch.empty(B, P, dtype=torch.float64).pin_memory()
+                out_host = torch.empty(B * (P + 2), dtype=torch.float64).pin_memory()
+                staging = torch.empty(self.lib.avn_gp_host_staging_bytes(self._h, B), dtype=torch.uint8, device=self.device)
+                ws = self._workspace(B)
+            h = out_host.numpy()
+            hc = self._hostcall = dict(B=B, ws=ws, th_host=th_host, th_np=th_host.numpy(), out_host=out_host, staging=staging,
+                                       ll=h[:B], grad=h[B:B + B * P].reshape(B, P), info=h[B + B * P:].view(np.int32)[:B],
+                                       args=(self._h, _ptr(th_host), B, _ptr(out_host)),
+                                       tail=(_ptr(staging), staging.numel(), _ptr(ws), ws.numel()))
+        hc['th_np'][...] = theta
+        rc = self.lib.avn_gp_loglik_grad_host(*hc['args'], 1 if want_grad else 0, *hc['tail'], self._stream())
+        if rc != 0:
+            raise GPError(_lib.last_error())
+        self.launches = self.lib.avn_gp_last_launch_count(self._h)
+        self._last_B = B
+        info = hc['info'].copy()
+        check_info(info, 'avn_gp_loglik_grad')
+        return hc['ll'].copy(), (hc['grad'].copy() if want_grad else None), info
+
+    @_on_device
+    def _loglik_grad_host_plain(self, theta, want_grad=True):
+        """the un-captured form of :meth:`loglik_grad_host`: pinned upload, ``avn_gp_loglik_grad`` on the current stream,
+        one packed device->host copy, one stream synchronisation."""
         B, P = theta.shape
         n = B * (P + 2)
         if getattr(self, '_pack', None) is None or self._pack.numel() != n:
@@ -220,15 +254,15 @@ class GPEngine:
             self._pack_host = torch.empty(n, dtype=torch.float64).pin_memory()
             self._theta_host = torch.empty(B, P, dtype=torch.float64).pin_memory()
         buf = self._pack
-        out = (buf[:B], buf[B:B + B * P].view(B, P), buf[B + B * P:].view(torch.int32)[:B])
+        out = (buf[:B], buf[B:B + B * P].view(B, P) if want_grad else None, buf[B + B * P:].view(torch.int32)[:B])
         self._theta_host.copy_(torch.from_numpy(theta))
-        self.loglik_grad(self._theta_host.to(self.device, non_blocking=True), out=out)
+        self.loglik_grad(self._theta_host.to(self.device, non_blocking=True), want_grad=want_grad, out=out)
         self._pack_host.copy_(buf, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         h = self._pack_host.numpy()
         info = h[B + B * P:].view(np.int32)[:B].copy()
         check_info(info, 'avn_gp_loglik_grad')
-        return h[:B].copy(), h[B:B + B * P].reshape(B, P).copy(), info
+        return h[:B].copy(), (h[B:B + B * P].reshape(B, P).copy() if want_grad else None), info
 
     @_on_device
     def cov(self, theta):

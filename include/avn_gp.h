@@ -131,6 +131,18 @@ int avn_gp_workspace_layout(const avn_gp* gp, int64_t B, avn_ws_layout* out);
 int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B, double* ll_dev, double* grad_dev,
                        int32_t* info_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* The same evaluation with HOST buffers -- the call pm.find_MAP / pm.sample make once per optimiser step or leapfrog
+ * (gpmcmc.py:332,345,351,357: a NumPy point in, logp and dlogp out).  theta_host [B,P] and out_host [B*(P+2)] are
+ * PINNED host memory; out_host receives ll [B], then grad [B,P], then info as int32 [B] in the low half of the last B
+ * doubles (one packed device->host copy).  staging_dev: avn_gp_host_staging_bytes(B) bytes of device memory for the
+ * points and the packed results.  The host->device copy, every launch and the device->host copy are captured ONCE as
+ * a CUDA graph on a library-owned stream (capture is not possible on the legacy default stream) and replayed by later
+ * calls with the same buffers, B and data; the replay is ordered behind the work already enqueued on `stream`, and the
+ * call returns when out_host is complete (SYNCHRONOUS, unlike the rest of this API).  want_grad = 0: value only. */
+size_t avn_gp_host_staging_bytes(const avn_gp* gp, int64_t B);
+int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int64_t B, double* out_host, int32_t want_grad,
+                            void* staging_dev, size_t staging_bytes, void* ws_dev, size_t ws_bytes, void* stream);
+
 /* Independent samples of one avn_gp_loglik_grad call are split into up to max_groups (1..8, default 4) groups that
  * run concurrently on library-owned streams, forked from and joined back into the caller's stream. */
 int avn_gp_set_streams(avn_gp* gp, int max_groups);

@@ -505,3 +505,33 @@ def test_packed_host_path_equals_device_path():
         assert np.array_equal(hi, info.cpu().numpy()) and hi.dtype == np.int32
         if B == 5:
             assert hi[3] > 0 and hl[3] == -np.inf and not np.any(hg[3])
+
+
+def test_captured_host_call_equals_device_path():
+    """avn_gp_loglik_grad_host (the CUDA graph of H2D + evaluation + packed D2H, replayed from the second call of a batch
+    size on) returns bit for bit what the device-tensor path returns: repeated calls with changing points, value-only
+    calls, a batch-size change, new training data (re-capture) and a non-PD sample inside the captured batch."""
+    spec = go.ModelSpec(nx=3, kerns=['Matern52'])
+    X, y, th, _ = cases.synth(spec, 150, seed=23)
+    eng = engine(spec)
+    eng.set_data(X, y)
+    rng = np.random.default_rng(1)
+    for B, reps in ((1, 4), (3, 3), (1, 2)):
+        for r in range(reps):
+            ths = np.stack([th * np.exp(0.1 * rng.normal(size=th.shape)) for _ in range(B)])
+            if B == 3 and r == 2:
+                ths[1, 0] = -1.0
+            ll, gr, info = eng.loglik_grad(ths)
+            hl, hg, hi = eng.loglik_grad_host(ths)
+            assert np.array_equal(hl, ll.cpu().numpy()) and np.array_equal(hg, gr.cpu().numpy())
+            assert np.array_equal(hi, info.cpu().numpy())
+            if r >= 1:
+                assert eng._hostcall['B'] == B           # the captured path was taken
+        hl2, hg2, _ = eng.loglik_grad_host(ths, want_grad=False)
+        assert hg2 is None and np.array_equal(hl2, hl)
+    eng.set_data(X[:120], y[:120])
+    for r in range(3):
+        ths = th[None, :] * (1.0 + 0.01 * r)
+        ll, gr, info = eng.loglik_grad(ths)
+        hl, hg, hi = eng.loglik_grad_host(ths)
+        assert np.array_equal(hl, ll.cpu().numpy()) and np.array_equal(hg, gr.cpu().numpy())

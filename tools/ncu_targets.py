@@ -32,7 +32,8 @@ else:
     (kw, X, y, th), ab = bench.workload_c4()
     eng = GPEngine(**kw, device=dev)
     eng.set_data(X, y)
-    eng.factorize(th)
+    info = eng.factorize(th)
+    print('factorize info', int(info[0]))
     M = 18944
     Xs = torch.as_tensor(bench.c4_test_points(M), device=dev)
     epi = GPEngine.make_epilogue(mode='revert', deg=8, yrev=[(T.OP_AFFINE_CONST, -1, (ab[0], ab[1], 0.0, 0.0))])
