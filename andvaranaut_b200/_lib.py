@@ -62,6 +62,7 @@ SYMBOLS = {
     'avn_gp_host_staging_bytes': (C.c_size_t, [C.c_void_p, C.c_int64]),
     'avn_gp_loglik_grad_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    'avn_gp_host_wait': (C.c_int, [C.c_void_p]),
     'avn_gp_set_streams': (C.c_int, [C.c_void_p, C.c_int]),
     'avn_gp_cov': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'avn_gp_state_bytes': (C.c_size_t, [C.c_void_p]),

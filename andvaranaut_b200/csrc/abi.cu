@@ -305,6 +305,8 @@ extern "C" int avn_gp_workspace_layout(const avn_gp* gp, int64_t B, avn_ws_layou
   return 0;
 }
 
+static const int64_t kWarpStageMaxBytes = 160 * 1024;   // shared-memory staging of a warped column (warp_kernel)
+
 template <typename K>
 static cudaError_t opt_in_smem(K kernel, size_t bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -347,6 +349,7 @@ static int ensure_ready(avn_gp* gp) {
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   if (cov_smem_bytes(kd) > 48 * 1024) chk(opt_in_smem(cov_kernel, cov_smem_bytes(kd)));
   chk(opt_in_smem(factor_kernel, FAC_SMEM_BYTES_FUSED));
+  chk(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpStageMaxBytes));
   if (kd.nkern == 1) {
     WsPtrs none{};
     int rc = launch_kinv_fast(true, kd.kern[0], gp->has_xwarp, dim3(1), kinv_fast_smem_bytes(kd), nullptr, kd, 0, 0, nullptr, none);
@@ -383,8 +386,15 @@ static int ensure_ready(avn_gp* gp) {
 // conversions + scaled inputs for B samples
 static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st) {
   Phase ph(gp, AVN_PH_WARP, st);
-  warp_kernel<<<dim3((unsigned)gp->kd.d + 1, (unsigned)B), 256, 0, st>>>(gp->kd, gp->progs, gp->X, gp->y, (int)gp->N,
-                                                                       (int)npad, theta, W);
+  // columns with a warp program are staged in shared memory when they fit (see warp_kernel)
+  int max_np = -1;
+  for (int m = 0; m < gp->kd.d; m++)
+    if (gp->progs.xw[m].nstages > 0 && gp->progs.xw[m].nparams > max_np) max_np = gp->progs.xw[m].nparams;
+  if (gp->progs.yw.nstages > 0 && gp->progs.yw.nparams > max_np) max_np = gp->progs.yw.nparams;
+  int64_t stage_doubles = max_np >= 0 ? gp->N * (1 + max_np) : 0;
+  if (stage_doubles * 8 > kWarpStageMaxBytes) stage_doubles = 0;
+  warp_kernel<<<dim3((unsigned)gp->kd.d + 1, (unsigned)B), 256, (size_t)stage_doubles * 8, st>>>(
+      gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W, (int)stage_doubles);
   LAUNCH_CHECK("warp_kernel");
   scale_kernel<<<dim3((unsigned)((npad + 255) / 256), (unsigned)B), 256, 0, st>>>(gp->kd, (int)npad, theta, W);
   LAUNCH_CHECK("scale_kernel");
@@ -632,7 +642,8 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
     gx_reduce_kernel<<<dim3((unsigned)((npad * kd.d + 255) / 256), (unsigned)Bg), 256, 0, st>>>((int)npad, kd.d, W.gxpart);
     LAUNCH_CHECK("gx_reduce_kernel");
   }
-  finalize_kernel<<<(unsigned)Bg, 256, 0, st>>>(kd, gp->progs, (int)gp->N, (int)npad, (int)ntiles, want_grad ? 1 : 0,
+  finalize_kernel<<<dim3((unsigned)Bg, (unsigned)finalize_grid_y(kd.n_iw, kd.n_cw, want_grad ? 1 : 0)), 256, 0, st>>>(
+      kd, gp->progs, (int)gp->N, (int)npad, (int)ntiles, want_grad ? 1 : 0,
                                                 theta, W, info, ll, grad);
   LAUNCH_CHECK("finalize_kernel");
   return 0;
@@ -704,8 +715,19 @@ extern "C" size_t avn_gp_host_staging_bytes(const avn_gp* gp, int64_t B) {
   return (size_t)(align_up(B * P * 8, 256) + align_up(B * (P + 2) * 8, 256));
 }
 
-extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int64_t B, double* out_host, int32_t want_grad,
+extern "C" int avn_gp_host_wait(avn_gp* gp) {
+  if (!gp) return fail("avn_gp_host_wait: null handle");
+  if (!gp->hstream) return 0;
+  DevGuard guard(gp);
+  cudaError_t e = cudaStreamSynchronize(gp->hstream);
+  if (e != cudaSuccess) return fail_cuda("avn_gp_host_wait", e);
+  return 0;
+}
+
+extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int64_t B, double* out_host, int32_t flags,
                                        void* staging_dev, size_t staging_bytes, void* ws_dev, size_t ws_bytes, void* stream) {
+  const int want_grad = flags & 1;
+  const bool no_wait = (flags & 2) != 0;
   if (!gp || !theta_host || !out_host || !staging_dev || !ws_dev) return fail("avn_gp_loglik_grad_host: null argument");
   if (gp->N < 1) return fail("avn_gp_loglik_grad_host: set_data first");
   if (B < 1 || B > 65535) return fail("avn_gp_loglik_grad_host: B out of range [1,65535]");
@@ -766,7 +788,7 @@ extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int
   e = cudaEventRecord(gp->hev, st);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(gp->hstream, gp->hev, 0);
   if (e == cudaSuccess) e = cudaGraphLaunch(gp->hexec, gp->hstream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(gp->hstream);
+  if (e == cudaSuccess && !no_wait) e = cudaStreamSynchronize(gp->hstream);
   if (e != cudaSuccess) return fail_cuda("graph launch", e);
   return 0;
 }

@@ -39,14 +39,24 @@ constexpr int WSTAT = 16;
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs, const double* __restrict__ X,
                                                    const double* __restrict__ y, int N, int npad,
-                                                   const double* __restrict__ theta, WsPtrs ws) {
+                                                   const double* __restrict__ theta, WsPtrs ws, int stage_doubles) {
+  // stage_doubles >= N (1 + nparams): the column and its parameter Jacobians live in dynamic shared memory while the
+  // stages of the warp program run over them (every stage is a pass over the column, the data-dependent ones several
+  // with block reductions between: on the strided global arrays each pass paid an L2 round trip per element -- 90 us of
+  // a 1.1 ms evaluation at B = 1) and are written to their global layout once at the end.  Same arithmetic either way.
+  extern __shared__ __align__(16) double wsm[];
   __shared__ double sh[128];
   const int b = blockIdx.y, m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const double* th = theta + (int64_t)b * kd.P;
   if (m < kd.d) {
     double* xw = ws.xw + (int64_t)b * npad * kd.d + m;
-    for (int n = tid; n < npad; n += nt) xw[(int64_t)n * kd.d] = (n < N) ? X[(int64_t)n * kd.d + m] : 0.0;
     const avn_warp_prog& pr = progs.xw[m];
+    const bool staged = pr.nstages > 0 && stage_doubles >= N * (1 + pr.nparams);
+    for (int n = tid; n < npad; n += nt) {
+      const double v = (n < N) ? X[(int64_t)n * kd.d + m] : 0.0;
+      if (staged && n < N) wsm[n] = v;
+      else xw[(int64_t)n * kd.d] = v;
+    }
     if (pr.nstages > 0) {
       int poff = 0;
       for (int q = 0; q < m; q++)
@@ -54,18 +64,46 @@ __global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs,
       __syncthreads();
       double dummy = 0, ddummy[MAXWP];
       double* dual = ws.dxw + ((int64_t)b * npad * kd.d + m) * MAXWP;
-      run_warp_column(pr, th + kd.off_iw + poff, N, xw, kd.d, dual, (int64_t)kd.d * MAXWP, 0, dummy, ddummy, sh);
+      if (staged) {
+        const int np = pr.nparams;
+        double* sdual = wsm + N;
+        run_warp_column(pr, th + kd.off_iw + poff, N, wsm, 1, sdual, np, 0, dummy, ddummy, sh);
+        __syncthreads();
+        for (int n = tid; n < N; n += nt) {
+          xw[(int64_t)n * kd.d] = wsm[n];
+          for (int q = 0; q < np; q++) dual[(int64_t)n * kd.d * MAXWP + q] = sdual[n * np + q];
+        }
+      } else {
+        run_warp_column(pr, th + kd.off_iw + poff, N, xw, kd.d, dual, (int64_t)kd.d * MAXWP, 0, dummy, ddummy, sh);
+      }
     }
     return;
   }
   double* z = ws.z + (int64_t)b * npad;
-  for (int n = tid; n < npad; n += nt) z[n] = (n < N) ? y[n] : 0.0;
+  const bool staged = progs.yw.nstages > 0 && stage_doubles >= N * (1 + progs.yw.nparams);
+  for (int n = tid; n < npad; n += nt) {
+    const double v = (n < N) ? y[n] : 0.0;
+    if (staged && n < N) wsm[n] = v;
+    else z[n] = v;
+  }
   __syncthreads();
   double* wst = ws.wstat + (int64_t)b * WSTAT;
   if (progs.yw.nstages > 0) {
     double lsum = 0, dlsum[MAXWP];
     for (int q = 0; q < MAXWP; q++) dlsum[q] = 0.0;
-    run_warp_column(progs.yw, th + kd.off_cw, N, z, 1, ws.dz + (int64_t)b * npad * MAXWP, MAXWP, 1, lsum, dlsum, sh);
+    double* dz = ws.dz + (int64_t)b * npad * MAXWP;
+    if (staged) {
+      const int np = progs.yw.nparams;
+      double* sdual = wsm + N;
+      run_warp_column(progs.yw, th + kd.off_cw, N, wsm, 1, sdual, np, 1, lsum, dlsum, sh);
+      __syncthreads();
+      for (int n = tid; n < N; n += nt) {
+        z[n] = wsm[n];
+        for (int q = 0; q < np; q++) dz[(int64_t)n * MAXWP + q] = sdual[n * np + q];
+      }
+    } else {
+      run_warp_column(progs.yw, th + kd.off_cw, N, z, 1, dz, MAXWP, 1, lsum, dlsum, sh);
+    }
     double tot = block_sum(lsum, sh);
     if (tid == 0) wst[0] = tot;
     for (int q = 0; q < progs.yw.nparams; q++) {
@@ -284,8 +322,21 @@ __global__ void __launch_bounds__(256) alpha_kernel(const double* __restrict__ T
   const int c = tid & 63, rg = tid >> 6;
   const double* T = Tall + (int64_t)b * npad * npad;
   const double* beta = beta_all + (int64_t)b * npad;
+  // sixteen loads in flight per thread, the sum itself in the same sequential order as a plain loop (with four in flight
+  // a single evaluation, 32 CTAs, was bound by its own L2 latency: 31 us for 16 MB)
   double acc = 0.0;
-  for (int i = j0 + rg; i < npad; i += 4) acc += T[(int64_t)i * npad + j0 + c] * beta[i];
+  int i = j0 + rg;
+  for (; i + 60 < npad; i += 64) {
+    double tv[16], bv[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      tv[u] = T[(int64_t)(i + 4 * u) * npad + j0 + c];
+      bv[u] = beta[i + 4 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) acc += tv[u] * bv[u];
+  }
+  for (; i < npad; i += 4) acc += T[(int64_t)i * npad + j0 + c] * beta[i];
   part[rg][c] = acc;
   __syncthreads();
   if (tid < TILE)
@@ -509,8 +560,16 @@ __global__ void __launch_bounds__(256) gx_reduce_kernel(int npad, int d, double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// finalisation: ll and gradient assembly.  grid (B), 256 threads.
+// finalisation: ll and gradient assembly.  grid (B, 1 + ceil(n_iw / 8) + ceil(n_cw / 8)), 256 threads: CTA y = 0 forms ll
+// and the kernel hyperparameter slots, the following CTAs take eight (dimension, parameter) pairs of the learnable input
+// warps each, the last ones eight output-warp parameters each -- one warp per pair as before (same summation order,
+// same bits), but the pairs of a sample no longer queue behind each other on ONE CTA (61 -> 2x us at B = 1, where this
+// kernel is latency-bound on strided L2 reads).
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int finalize_grid_y(int n_iw, int n_cw, int want_grad) {
+  return want_grad ? 1 + (n_iw + 7) / 8 + (n_cw + 7) / 8 : 1;
+}
+
 __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs progs, int N, int npad, int ntiles,
                                                        int want_grad, const double* __restrict__ theta, WsPtrs ws,
                                                        int32_t* __restrict__ info, double* __restrict__ ll,
@@ -523,54 +582,71 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   // info = -1 with ll = NaN and a zero gradient -- distinct from a non-positive pivot (info > 0, ll = -inf).
   const bool aborted = ws.ctl[1] != 0;
   const bool bad = aborted || info[b] != 0;
-  if (aborted) {
-    __syncthreads();   // every thread has read info[b]
+  const int role = blockIdx.y, n_iw_ctas = (kd.n_iw + 7) / 8;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int d = kd.d, nk = kd.nkern;
+  double* gr = want_grad ? grad + (int64_t)b * kd.P : nullptr;
+  if (role == 0) {
+    if (aborted) {
+      // info[b] is rewritten here: the other CTAs of the sample take `bad` from the abort flag itself
+      if (tid == 0) {
+        info[b] = -1;
+        ll[b] = NAN;
+      }
+    } else if (tid == 0) {
+      const double norm = -0.5 * N * 1.8378770664093454835606594728112;  // log(2 pi)
+      const int nbk = npad / TILE;
+      const double* fp = ws.fpart + (int64_t)b * nbk * 2;
+      double quad = 0.0, logdet = 0.0;   // fixed order: deterministic
+      for (int k = 0; k < nbk; k++) {
+        quad += fp[2 * k];
+        logdet += fp[2 * k + 1];
+      }
+      double v = (norm - 0.5 * quad) - logdet + wst[0];
+      ll[b] = bad ? -INFINITY : v;
+    }
+    if (!want_grad) return;
+    if (bad) {
+      for (int e = tid; e < kd.off_iw; e += 256) gr[e] = 0.0;
+      if (tid == 0 && kd.has_alpha) gr[kd.off_alpha] = 0.0;
+      return;
+    }
+    const int nacc = nk * d + nk + 2;
+    for (int e = warp; e < nacc; e += 8) {  // one warp per slot, lanes stride over tiles (fixed order: deterministic)
+      double s = 0.0;
+      const double* gp = ws.gpart + (int64_t)b * ntiles * MAXACC + e;
+      for (int tI = lane; tI < ntiles; tI += 32) s += gp[(int64_t)tI * MAXACC];
+      s = warp_sum(s);
+      if (lane == 0) slots[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < nk * d; e += 256) gr[kd.off_l + e] = -slots[e] / th[kd.off_l + e];
+    if (tid < nk) gr[kd.off_kv + tid] = 0.5 * slots[nk * d + tid];
     if (tid == 0) {
-      info[b] = -1;
-      ll[b] = NAN;
+      if (kd.noise) gr[kd.off_gv] = 0.5 * slots[nk * d + nk];
+      if (kd.has_alpha) gr[kd.off_alpha] = 0.5 * slots[nk * d + nk + 1];
     }
-  } else if (tid == 0) {
-    const double norm = -0.5 * N * 1.8378770664093454835606594728112;  // log(2 pi)
-    const int nbk = npad / TILE;
-    const double* fp = ws.fpart + (int64_t)b * nbk * 2;
-    double quad = 0.0, logdet = 0.0;   // fixed order: deterministic
-    for (int k = 0; k < nbk; k++) {
-      quad += fp[2 * k];
-      logdet += fp[2 * k + 1];
-    }
-    double v = (norm - 0.5 * quad) - logdet + wst[0];
-    ll[b] = bad ? -INFINITY : v;
-  }
-  if (!want_grad) return;
-  double* gr = grad + (int64_t)b * kd.P;
-  if (bad) {
-    for (int e = tid; e < kd.P; e += 256) gr[e] = 0.0;
     return;
   }
-  const int d = kd.d, nk = kd.nkern;
-  const int nacc = nk * d + nk + 2;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int e = warp; e < nacc; e += 8) {  // one warp per slot, lanes stride over tiles (fixed order: deterministic)
-    double s = 0.0;
-    const double* gp = ws.gpart + (int64_t)b * ntiles * MAXACC + e;
-    for (int tI = lane; tI < ntiles; tI += 32) s += gp[(int64_t)tI * MAXACC];
-    s = warp_sum(s);
-    if (lane == 0) slots[e] = s;
-  }
-  __syncthreads();
-  for (int e = tid; e < nk * d; e += 256) gr[kd.off_l + e] = -slots[e] / th[kd.off_l + e];
-  if (tid < nk) gr[kd.off_kv + tid] = 0.5 * slots[nk * d + tid];
-  if (tid == 0) {
-    if (kd.noise) gr[kd.off_gv] = 0.5 * slots[nk * d + nk];
-    if (kd.has_alpha) gr[kd.off_alpha] = 0.5 * slots[nk * d + nk + 1];
+  if (!want_grad) return;
+  if (bad) {
+    // this CTA's slice of the warp-parameter gradient
+    if (role <= n_iw_ctas) {
+      const int pq = (role - 1) * 8 + warp;
+      if (lane == 0 && pq < kd.n_iw) gr[kd.off_iw + pq] = 0.0;
+    } else {
+      const int q = (role - 1 - n_iw_ctas) * 8 + warp;
+      if (lane == 0 && q < kd.n_cw) gr[kd.off_cw + q] = 0.0;
+    }
+    return;
   }
   // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p.  One warp per (dimension, parameter) pair -- all pairs
   // dealt to the 8 warps at once -- lanes stride over n (four rows in flight), one shuffle reduction, no barrier.
-  if (kd.n_iw > 0) {
+  if (role <= n_iw_ctas) {
     const int nb = npad / TILE;
     // G[n][m] = sum over source tiles, already reduced into slab 0 by gx_reduce_kernel
     const double* G = ws.gxpart + (int64_t)b * nb * npad * d;
-    for (int pq = warp; pq < kd.n_iw; pq += 8) {
+    for (int pq = (role - 1) * 8 + warp; pq < min(kd.n_iw, role * 8); pq += 8) {
       // pair index -> (dimension m, parameter q of its warp)
       int m = 0, q = pq;
       for (;; m++) {
@@ -599,9 +675,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
     }
   }
   // learnable output warp: -alpha^T dz/dp + sum d log g'/dp
-  if (kd.n_cw > 0) {
+  if (role > n_iw_ctas) {
     const double* al = ws.alpha + (int64_t)b * npad;
-    for (int q = warp; q < kd.n_cw; q += 8) {
+    const int r0 = role - 1 - n_iw_ctas;
+    for (int q = r0 * 8 + warp; q < min(kd.n_cw, (r0 + 1) * 8); q += 8) {
       const double* Dz = ws.dz + (int64_t)b * npad * MAXWP + q;
       double a[4] = {0.0, 0.0, 0.0, 0.0};
       int n = lane;

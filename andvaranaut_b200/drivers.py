@@ -37,16 +37,25 @@ class Posterior:
         theta, dxdz, ljac, dljac = self.space.theta_from_z(z)
         if self.shard is not None:
             ll, gll, info = self.shard.loglik_grad(self.engine, theta)
+            lp, glp = self.space.prior(theta)
+        elif hasattr(self.engine, 'loglik_grad_host_begin'):
+            # the device evaluates (captured graph: upload, launches, one packed download) while the host forms the priors
+            token = self.engine.loglik_grad_host_begin(theta)
+            try:
+                lp, glp = self.space.prior(theta)
+            finally:
+                ll, gll, info = self.engine.loglik_grad_host_end(token)
         elif hasattr(self.engine, 'loglik_grad_host'):
-            ll, gll, info = self.engine.loglik_grad_host(theta)      # one packed device->host copy
+            ll, gll, info = self.engine.loglik_grad_host(theta)
+            lp, glp = self.space.prior(theta)
         else:
             ll_t, g_t, info_t = self.engine.loglik_grad(theta)
             ll, gll, info = ll_t.cpu().numpy(), g_t.cpu().numpy(), info_t.cpu().numpy()
             if np.any(info < 0):
                 raise RuntimeError('avn_gp_loglik_grad: factorisation aborted on the device (info = -1)')
+            lp, glp = self.space.prior(theta)
         self.n_eval += z.shape[0]
         self.n_calls += 1
-        lp, glp = self.space.prior(theta)
         val = ll + lp
         with np.errstate(all='ignore'):
             grad = self.space.grad_theta_to_z(gll + glp, dxdz)

@@ -207,7 +207,7 @@ class GPEngine:
         self._last_B = B
         return ll, grad, info
 
-    def loglik_grad_host(self, theta, want_grad=True):
+    def loglik_grad_host(self, theta, want_grad=True, _async=False):
         """host arrays in, host arrays out: theta [B,P] NumPy -> (ll [B], grad [B,P], info [B]) NumPy -- the call the
         optimiser / sampler drivers make once per step.  From the second consecutive call with the same batch size on
         it goes through ``avn_gp_loglik_grad_host``: the point is written into a pinned host buffer and the host->device
@@ -234,14 +234,36 @@ class GPEngine:
                                        args=(self._h, _ptr(th_host), B, _ptr(out_host)),
                                        tail=(_ptr(staging), staging.numel(), _ptr(ws), ws.numel()))
         hc['th_np'][...] = theta
-        rc = self.lib.avn_gp_loglik_grad_host(*hc['args'], 1 if want_grad else 0, *hc['tail'], self._stream())
+        hc['want_grad'] = want_grad
+        rc = self.lib.avn_gp_loglik_grad_host(*hc['args'], (1 if want_grad else 0) | (2 if _async else 0), *hc['tail'],
+                                              self._stream())
         if rc != 0:
             raise GPError(_lib.last_error())
         self.launches = self.lib.avn_gp_last_launch_count(self._h)
         self._last_B = B
+        if _async:
+            return hc
+        return self._host_results(hc)
+
+    @staticmethod
+    def _host_results(hc):
         info = hc['info'].copy()
         check_info(info, 'avn_gp_loglik_grad')
-        return hc['ll'].copy(), (hc['grad'].copy() if want_grad else None), info
+        return hc['ll'].copy(), (hc['grad'].copy() if hc['want_grad'] else None), info
+
+    def loglik_grad_host_begin(self, theta, want_grad=True):
+        """asynchronous form of :meth:`loglik_grad_host` for the drivers: the evaluation is launched and the call returns a
+        token; the caller computes its host-side terms (priors, Jacobians) while the device works and collects
+        (ll, grad, info) with :meth:`loglik_grad_host_end`.  Batch sizes not yet captured are evaluated at once."""
+        out = self.loglik_grad_host(theta, want_grad, _async=True)
+        return out
+
+    def loglik_grad_host_end(self, token):
+        if isinstance(token, tuple):          # evaluated synchronously (first call of a batch size)
+            return token
+        if self.lib.avn_gp_host_wait(self._h) != 0:
+            raise GPError(_lib.last_error())
+        return self._host_results(token)
 
     @_on_device
     def _loglik_grad_host_plain(self, theta, want_grad=True):

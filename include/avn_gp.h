@@ -138,10 +138,14 @@ int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B, double* l
  * points and the packed results.  The host->device copy, every launch and the device->host copy are captured ONCE as
  * a CUDA graph on a library-owned stream (capture is not possible on the legacy default stream) and replayed by later
  * calls with the same buffers, B and data; the replay is ordered behind the work already enqueued on `stream`, and the
- * call returns when out_host is complete (SYNCHRONOUS, unlike the rest of this API).  want_grad = 0: value only. */
+ * call returns when out_host is complete (SYNCHRONOUS, unlike the rest of this API).
+ * flags: bit 0 = gradient wanted (0: value only); bit 1 = return right after the launch -- the caller does its own host
+ * work (the prior terms of the posterior, gpmcmc.py:193-208) meanwhile and completes the call with avn_gp_host_wait;
+ * theta_host / out_host must not be touched in between. */
 size_t avn_gp_host_staging_bytes(const avn_gp* gp, int64_t B);
-int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int64_t B, double* out_host, int32_t want_grad,
+int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int64_t B, double* out_host, int32_t flags,
                             void* staging_dev, size_t staging_bytes, void* ws_dev, size_t ws_bytes, void* stream);
+int avn_gp_host_wait(avn_gp* gp);
 
 /* Independent samples of one avn_gp_loglik_grad call are split into up to max_groups (1..8, default 4) groups that
  * run concurrently on library-owned streams, forked from and joined back into the caller's stream. */

@@ -529,6 +529,10 @@ def test_captured_host_call_equals_device_path():
                 assert eng._hostcall['B'] == B           # the captured path was taken
         hl2, hg2, _ = eng.loglik_grad_host(ths, want_grad=False)
         assert hg2 is None and np.array_equal(hl2, hl)
+        # asynchronous form used by the drivers: launch, host work meanwhile, collect
+        tok = eng.loglik_grad_host_begin(ths)
+        al, ag, ai = eng.loglik_grad_host_end(tok)
+        assert np.array_equal(al, hl) and np.array_equal(ag, hg) and np.array_equal(ai, hi)
     eng.set_data(X[:120], y[:120])
     for r in range(3):
         ths = th[None, :] * (1.0 + 0.01 * r)
