@@ -273,8 +273,8 @@ static void layout(const avn_gp* gp, int64_t B, avn_ws_layout* L) {
   L->gpart = take(B * ntiles * MAXACC);
   L->gxpart = take(gp->has_xwarp ? B * nb * npad * kd.d : 0);
   L->fpart = take(B * nb * 2);
-  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], 8 control words per stream group, sflag [B][nb]
-  L->fflags = take((3 * B * nb + 8 * 8 + 1) / 2);
+  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], 8 control words per stream group, sflag [B][nb], dflag [B][nb]
+  L->fflags = take((4 * B * nb + 8 * 8 + 1) / 2);
   L->total = off;
 }
 
@@ -289,6 +289,7 @@ static WsPtrs ws_ptrs(const avn_ws_layout& L, void* ws, int64_t B) {
   p.tflag = p.lflag + B * L.nb;
   p.ctl = p.tflag + B * L.nb;
   p.sflag = p.ctl + 64;
+  p.dflag = p.sflag + B * L.nb;
   return p;
 }
 
@@ -348,7 +349,8 @@ static int ensure_ready(avn_gp* gp) {
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   if (cov_smem_bytes(kd) > 48 * 1024) chk(opt_in_smem(cov_kernel, cov_smem_bytes(kd)));
-  chk(opt_in_smem(factor_kernel, FAC_SMEM_BYTES_FUSED));
+  chk(opt_in_smem(factor_kernel<false>, FAC_SMEM_BYTES));
+  chk(opt_in_smem(factor_kernel<true>, FAC_SMEM_BYTES_FUSED));
   chk(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpStageMaxBytes));
   if (kd.nkern == 1) {
     WsPtrs none{};
@@ -371,11 +373,11 @@ static int ensure_ready(avn_gp* gp) {
   if (e != cudaSuccess) return fail_cuda("shared-memory opt-in", e);
   int sms = 0, per_sm = 0;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gp->device);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel<false>, FAC_THREADS, FAC_SMEM_BYTES);
   if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
   gp->fac_resident = sms * per_sm;
   int per_sm_f = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, factor_kernel, FAC_THREADS, FAC_SMEM_BYTES_FUSED);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, factor_kernel<true>, FAC_THREADS, FAC_SMEM_BYTES_FUSED);
   if (e != cudaSuccess || per_sm_f < 1) return fail_cuda("factor occupancy (fused panel)", e);
   gp->fac_resident_fused = sms * per_sm_f;
   if (const char* env = getenv("AVN_FAC_CTAS_PER_SM")) gp->fac_resident = sms * atoi(env);   // development knob
@@ -441,7 +443,7 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
   const size_t smem = fused ? FAC_SMEM_BYTES_FUSED : FAC_SMEM_BYTES;
   FactorArgs fa;
   fa.L = W.kl; fa.T = W.t; fa.fpart = W.fpart; fa.info = info; fa.z = W.z; fa.beta = W.beta;
-  fa.lflag = W.lflag; fa.tflag = W.tflag; fa.sflag = W.sflag; fa.ctl = W.ctl;
+  fa.lflag = W.lflag; fa.tflag = W.tflag; fa.sflag = W.sflag; fa.dflag = W.dflag; fa.ctl = W.ctl;
   fa.npad = (int)npad; fa.nb = nb; fa.B = (int)B; fa.n = (int)gp->N; fa.want_inverse = want_inverse ? 1 : 0;
   fa.max_spins = gp->max_spins;
   fa.fault = gp->fault;
@@ -457,7 +459,8 @@ static int run_factor(avn_gp* gp, int64_t B, const WsPtrs& W, int32_t* info, int
 #endif
   {
     Phase ph(gp, AVN_PH_FACTOR, st);
-    factor_kernel<<<grid, FAC_THREADS, smem, st>>>(fa);
+    if (fused) factor_kernel<true><<<grid, FAC_THREADS, smem, st>>>(fa);
+    else factor_kernel<false><<<grid, FAC_THREADS, smem, st>>>(fa);
     LAUNCH_CHECK("factor_kernel");
   }
 #ifdef AVN_FACTOR_PROF
@@ -515,7 +518,7 @@ static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, 
 }
 
 static cudaError_t zero_flags(const WsPtrs& W, int64_t B, int64_t nb, cudaStream_t st) {
-  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(3 * B * nb + 64), st);
+  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(4 * B * nb + 64), st);
 }
 
 extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
@@ -557,6 +560,7 @@ static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& 
   p.lflag += b0 * nb;
   p.tflag += b0 * nb;
   p.sflag += b0 * nb;
+  p.dflag += b0 * nb;
   return p;
 }
 

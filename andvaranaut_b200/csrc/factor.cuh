@@ -87,6 +87,7 @@ struct FactorArgs {
   int32_t* lflag;       // [B][nb]
   int32_t* tflag;       // [B][nb]
   int32_t* sflag;       // [B][nb]  fused-panel launches: 1 = S of the tile (i, i-1) is parked in the T slab
+  int32_t* dflag;       // [B][nb]  fused-panel launches: 1 = Dpre(b,i) has left the partial diagonal block in place of A_ii
   int32_t* ctl;         // [0] ticket counter, [1] abort flag (a wait exceeded its bound)
   int npad, nb, B;
   int n;                // valid rows (N <= npad): tiles of the last block row skip their padding fragments
@@ -137,6 +138,8 @@ struct SlabWaiter {
   int* s_known;
   int m0, known;
   unsigned max_spins;
+  const int32_t* fc = nullptr;   // optional third flag with its own threshold (the chain's combined wait)
+  int need_c = 0;
   __device__ __forceinline__ void operator()(int kt) {
     if (kt % FAC_SPB) return;
     const int need = m0 + kt / FAC_SPB + 1;
@@ -147,6 +150,7 @@ struct SlabWaiter {
       for (;;) {
         const int va = ld_acquire(fa), vb = ld_acquire(fb);
         have = va < vb ? va : vb;
+        if (fc && ld_acquire(fc) < need_c) have = 0;
         if (have >= need) break;
         __nanosleep(AVN_POLL_NS);
         if ((++spins & 1023u) == 0) {
@@ -231,6 +235,15 @@ __device__ __forceinline__ void stage_tile(double* s, const double* __restrict__
   for (int q = 0; q < PER; q++) {
     const int e = threadIdx.x + q * FAC_THREADS, r = e >> 5, c = (e & 31) * 2;
     *reinterpret_cast<double2*>(&s[r * FAC_LDS + c]) = v[q];
+  }
+}
+
+// the same copy by cp.async (L2 -> shared memory, no registers): the caller commits the group and waits for it later
+__device__ __forceinline__ void stage_tile_async(double* s, const double* __restrict__ g, int64_t ld) {
+#pragma unroll
+  for (int q = 0; q < TILE * TILE / 2 / FAC_THREADS; q++) {
+    const int e = threadIdx.x + q * FAC_THREADS, r = e >> 5, c = (e & 31) * 2;
+    cp_async16(s + r * FAC_LDS + c, g + (int64_t)r * ld + c);
   }
 }
 
@@ -512,12 +525,101 @@ __device__ __forceinline__ void diag_chol_inv_blocked(double* sA, double* sT, do
   DPROF(12);
 }
 
+// blk -= X X^T on the 36 8 x 8 fragments (fi >= fj) of the lower triangle of a 64 x 64 block, X staged in shared memory
+// (pitch FAC_LDS); the last-slab update of a diagonal task, on the critical path of a single factorisation.  Nine
+// fragments per warp, register-blocked: warps 0..2 take the 3 x 3 rectangles rows {5,6,7} x columns {0,1,2}, rows {2,3,4}
+// x columns {0,1,2}, rows {5,6,7} x columns {3,4,5}; warp 3 the three 2 x 2 triangles at 0, 3 and 6 -- six operand
+// fragments feed nine DMMAs per 4-deep step (one fragment at a time needed 18 and sat at ~60 cycles per DMMA on their
+// latency), eighteen independent accumulator chains.  Per fragment: two accumulator pairs taking the even / odd 4-deep
+// steps, summed at the end -- the order every earlier version used, so the bits are unchanged.
+__device__ __forceinline__ void diag_update_blocked(double* blk, const double* sX, int warp, int gq, int t) {
+  int fr[3], fc[3];
+  if (warp < 3) {
+    const int r0 = (warp == 1) ? 2 : 5, c0 = (warp == 2) ? 3 : 0;
+#pragma unroll
+    for (int u = 0; u < 3; u++) { fr[u] = r0 + u; fc[u] = c0 + u; }
+    double acc[3][3][4];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < TILE; kk += 8) {
+      double a[3][2], b[3][2];
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        a[u][0] = sX[(8 * fr[u] + gq) * FAC_LDS + kk + t];
+        a[u][1] = sX[(8 * fr[u] + gq) * FAC_LDS + kk + 4 + t];
+        b[u][0] = sX[(8 * fc[u] + gq) * FAC_LDS + kk + t];
+        b[u][1] = sX[(8 * fc[u] + gq) * FAC_LDS + kk + 4 + t];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          dmma884(acc[i][j][0], acc[i][j][1], a[i][0], b[j][0]);
+          dmma884(acc[i][j][2], acc[i][j][3], a[i][1], b[j][1]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        double2* dst = reinterpret_cast<double2*>(&blk[(8 * fr[i] + gq) * FAC_LDS + 8 * fc[j] + 2 * t]);
+        double2 cur = *dst;
+        cur.x -= acc[i][j][0] + acc[i][j][2];
+        cur.y -= acc[i][j][1] + acc[i][j][3];
+        *dst = cur;
+      }
+  } else {
+    // triangles {(f,f), (f+1,f), (f+1,f+1)}, f = 0, 3, 6: operand fragments f and f+1
+    double acc[3][3][4];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < TILE; kk += 8) {
+      double x[3][2][2];   // [triangle][fragment f / f+1][even / odd step]
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+          x[u][v][0] = sX[(8 * (3 * u + v) + gq) * FAC_LDS + kk + t];
+          x[u][v][1] = sX[(8 * (3 * u + v) + gq) * FAC_LDS + kk + 4 + t];
+        }
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        dmma884(acc[u][0][0], acc[u][0][1], x[u][0][0], x[u][0][0]);   // (f, f)
+        dmma884(acc[u][0][2], acc[u][0][3], x[u][0][1], x[u][0][1]);
+        dmma884(acc[u][1][0], acc[u][1][1], x[u][1][0], x[u][0][0]);   // (f+1, f)
+        dmma884(acc[u][1][2], acc[u][1][3], x[u][1][1], x[u][0][1]);
+        dmma884(acc[u][2][0], acc[u][2][1], x[u][1][0], x[u][1][0]);   // (f+1, f+1)
+        dmma884(acc[u][2][2], acc[u][2][3], x[u][1][1], x[u][1][1]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; u++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int fi = 3 * u + (q > 0), fj = 3 * u + (q > 1);
+        double2* dst = reinterpret_cast<double2*>(&blk[(8 * fi + gq) * FAC_LDS + 8 * fj + 2 * t]);
+        double2 cur = *dst;
+        cur.x -= acc[u][q][0] + acc[u][q][2];
+        cur.y -= acc[u][q][1] + acc[u][q][3];
+        *dst = cur;
+      }
+  }
+}
+
 // X = S T_kk^T on 8 x 8 fragments, S and T_kk staged in shared memory (pitch FAC_LDS).  T_kk is lower triangular: the
 // fragment column jf needs k < 8 jf + 8 only.  Warp w takes the fragment columns w and 7 - w (18 four-deep steps per row
 // fragment between them, the same for every warp) and all eight row fragments: 144 DMMAs per warp, against 128 / 256
 // with the 32 x 32 quadrant layout.  xa[ii][c] = fragment (row ii, column c ? 7 - w : w).
 __device__ __forceinline__ void panel_product(double (&xa)[8][2][2], const double* sS, const double* sTk, int warp, int gq,
                                               int t) {
+  // (a variant that shared the S fragments between the two columns and loaded the operands of step k + 4 before the
+  // DMMAs of step k was slower, 3.9 us against 2.3 us in a diagonal chain and +2 % on throughput launches: registers)
 #pragma unroll
   for (int ii = 0; ii < 8; ii++) xa[ii][0][0] = xa[ii][0][1] = xa[ii][1][0] = xa[ii][1][1] = 0.0;
 #pragma unroll
@@ -533,7 +635,10 @@ __device__ __forceinline__ void panel_product(double (&xa)[8][2][2], const doubl
   }
 }
 
-__global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
+// FUSED: the fused-panel / chain launch for few samples (fa.fuse_panel == 1); its own instantiation, so that the
+// throughput kernel keeps the register allocation it had before the chain code existed (160 registers, no spills)
+template <bool FUSED>
+__global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(FactorArgs fa) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_ticket;
   __shared__ int s_known;
@@ -554,7 +659,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
   // everything it waits on has finished.
   // Throughput launches only: with few samples the CTAs run far ahead of the chain of diagonal tasks and mostly wait, and
   // a ticket held behind a waiting task would keep the next link of that chain from starting.
-  const bool prefetch = !fa.fuse_panel;
+  constexpr bool prefetch = !FUSED;
   int next_ticket = 0;
   if (tid == 0 && prefetch) next_ticket = atomicAdd(fa.ctl, 1);
   for (;;) {
@@ -594,151 +699,181 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
     int32_t* lflag = fa.lflag + (int64_t)b * nb;
     int32_t* tflag = fa.tflag + (int64_t)b * nb;
     const int rows_k = min(TILE, fa.n - k0);   // valid rows of block row k
-    if (type == 0) {
-      // ---------------- D(b,k) ----------------
+    if (type == 0 && FUSED && k > 0) {
+      // ---------------- Dpre(b,k): fused-panel launches ----------------
+      // the part of a diagonal task that does not depend on block column k-1: A_kk - sum_{m<k-1} L[k,m] L[k,m]^T, left in
+      // place of A_kk for the sample's chain CTA (below), which applies the last block column itself
       double* Akk = L + (int64_t)k0 * npad + k0;
-      double* Tkk = T + (int64_t)k0 * npad + k0;
-      FEVENT(0, k, 0);
-      // Few samples (fa.fuse_panel: fewer tile tasks per step than resident CTAs, the chain of diagonal tasks IS the run
-      // time): this task forms the panel tile L[k,k-1] = S T_mm^T (m = k - 1) itself, in shared memory, from the S that
-      // P(b,m,k) accumulated and parked (sflag), instead of waiting for P(b,m,k) to see T_mm, multiply, store, publish
-      // and then fetching the tile back -- between two diagonal factorisations that is one flag hop, one tile store +
-      // release and one staging round less.  P(b,m,k) still finishes the tile (everybody else reads it from L); the product
-      // is the same code on the same operands, so both modes give the same bits.  The launch then carries a third
-      // 64 x 64 tile of shared memory (2 CTAs per SM).
-      const bool fuse = fa.fuse_panel && k > 0;
-      double* blk = fuse ? smem + 2 * TILE * FAC_LDS : sA;   // the diagonal block: A_kk updated, then L_kk
-      double* tin = fuse ? sA : sB;                          // receives T_kk
       FacKK g;
       load_neg_tile(g.acc, Akk, npad, wm, wn, gq, t);
-      if (k > 0) {
-        // only the lower triangle of the block is used: the warp of the upper-right quadrant computes nothing
+      if (k > 1) {
         const bool idle_quadrant = (wm == 0 && wn == 1);
-        if (k > 1) {
-          // block columns 0 .. k-2 of row k through the pipeline: final long before this task is on the critical path
-          SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins};
-          g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0 - TILE,
-                [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
-        }
+        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins};
+        g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0 - TILE,
+              [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
       }
-      // the block as updated so far (A - sum over block columns 0 .. k-2) goes to shared memory ...
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-          *reinterpret_cast<double2*>(&blk[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
+          *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
         }
-      if (fuse) {
-        // S = A[k,m] - sum_{c<m} L[k,c] L[m,c]^T was parked by P(b,m,k) in the still unused tile (k,m) of the T slab (R(b,k,m)
-        // writes it only after this task has published T_kk) long before T_mm exists: fetched while D(b,m) factorises ...
-        const int m0 = k0 - TILE;
-        wait_flag(fa.sflag + (int64_t)b * nb + k, 1, fa.ctl, fa.max_spins);
-        stage_tile(sA, T + (int64_t)k0 * npad + m0, npad);
-        // ... then T_mm (the one thing the chain waits for), the product, and X stays in shared memory
-        FEVENT(0, k, 4);
-        wait_flag(lflag + k - 1, k, fa.ctl, fa.max_spins);
-        FEVENT(0, k, 5);
-        stage_tile(sB, T + (int64_t)m0 * npad + m0, npad);
-        __syncthreads();
-        double xa[8][2][2];
-        panel_product(xa, sA, sB, warp, gq, t);
-        __syncthreads();   // everyone has read S and T_mm
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const int jf = c ? 7 - warp : warp;
-#pragma unroll
-          for (int ii = 0; ii < 8; ii++)
-            *reinterpret_cast<double2*>(&sB[(8 * ii + gq) * FAC_LDS + 8 * jf + 2 * t]) = make_double2(xa[ii][c][0], xa[ii][c][1]);
-        }
-        __syncthreads();
-        FEVENT(0, k, 6);
-      } else if (k > 0) {
-        // ... and block column k-1, what the whole factorisation waits for (published by the panel task of the previous
-        // step), is applied there: the 64 x 64 tile L[k,k-1] is fetched in ONE round of loads (sixteen 16-byte loads in
-        // flight per thread, instead of four pipeline slabs issued two at a time)
-        FEVENT(0, k, 4);
-        wait_flag(lflag + k, k, fa.ctl, fa.max_spins);
-        FEVENT(0, k, 5);
-        stage_tile(sB, L + (int64_t)k0 * npad + (k0 - TILE), npad);
-        __syncthreads();
-        FEVENT(0, k, 6);
-      }
-      if (k > 0) {
-        // the update with block column k-1 runs on the 36 8 x 8 fragments of the lower triangle only, nine per warp (the
-        // 32 x 32 quadrant layout of the pipeline computes 48 fragments on three warps);
-        // three fragments in flight per warp (six independent accumulator chains; one fragment at a time left the warp
-        // waiting on an 8-deep dependent DMMA chain: this update is on the critical path of a single factorisation).
-        // Per fragment the order of the DMMAs is unchanged, so the result is bit-identical to the one-at-a-time loop.
-        for (int q0 = warp; q0 < 36; q0 += 3 * (FAC_THREADS / 32)) {
-          const double* pa[3];
-          const double* pb[3];
-          double2* dst[3];
-          double acc[3][4];
-#pragma unroll
-          for (int u = 0; u < 3; u++) {
-            const int q = q0 + u * (FAC_THREADS / 32);   // < 36: nine fragments per warp
-            int fi = 0;
-            while ((fi + 1) * (fi + 2) / 2 <= q) fi++;
-            const int fj = q - fi * (fi + 1) / 2;
-            pa[u] = sB + (8 * fi + gq) * FAC_LDS + t;
-            pb[u] = sB + (8 * fj + gq) * FAC_LDS + t;
-            dst[u] = reinterpret_cast<double2*>(&blk[(8 * fi + gq) * FAC_LDS + 8 * fj + 2 * t]);
-            acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
+      publish(fa.dflag + (int64_t)b * nb + k, 1);
+      FPROF(2);
+    } else if (type == 0) {
+      // ---------------- D(b,k) ----------------
+      // Throughput launches: one diagonal task per ticket.  Fused-panel launches (few samples: fewer tile tasks per step
+      // than resident CTAs, the chain of diagonal tasks IS the run time): the CTA that draws D(b,0) becomes the CHAIN of
+      // sample b and factorises every diagonal block k = 0 .. nb-1 itself, keeping T_kk in shared memory for the next
+      // link: it forms the panel tile L[k,k-1] = S T_mm^T (m = k-1) from the S that P(b,m,k) accumulated and parked in
+      // the still unused tile (k,m) of the T slab (sflag; R(b,k,m) writes that tile only after T_kk is published) and from
+      // its own T_mm, applies it to the partial block left by Dpre(b,k) (dflag) and factorises -- between two diagonal
+      // factorisations there is no flag hop, no release and no trip through L2 left, only the two products.  P(b,m,k)
+      // still finishes the tile for everybody else; products and update are the same code on the same operands as in
+      // throughput launches, so both modes give the same bits.  Such launches carry a third 64 x 64 tile of shared memory.
+      constexpr bool chain = FUSED;
+      double* blk = chain ? smem + 2 * TILE * FAC_LDS : sA;   // the diagonal block: A_kk updated, then L_kk
+      double* tin = chain ? sA : sB;                          // receives T_kk
+      const int k_end = chain ? nb : k + 1;
+      for (int kc = k; kc < k_end; kc++) {
+        const int c0 = kc * TILE;
+        const int rows_c = min(TILE, fa.n - c0);
+        double* Akk = L + (int64_t)c0 * npad + c0;
+        double* Tkk = T + (int64_t)c0 * npad + c0;
+        FEVENT(0, kc, 0);
+        if (!chain) {
+          FacKK g;
+          load_neg_tile(g.acc, Akk, npad, wm, wn, gq, t);
+          if (kc > 1) {
+            // only the lower triangle of the block is used: the warp of the upper-right quadrant computes nothing;
+            // block columns 0 .. k-2 of row k through the pipeline: final long before this task is on the critical path
+            const bool idle_quadrant = (wm == 0 && wn == 1);
+            SlabWaiter w{lflag + kc, lflag + kc, fa.ctl, &s_known, 0, 0, fa.max_spins};
+            g.run(smem, L + (int64_t)c0 * npad, npad, rows_c, L + (int64_t)c0 * npad, npad, 64, c0 - TILE,
+                  [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
           }
+          // the block as updated so far (A - sum over block columns 0 .. k-2) goes to shared memory ...
 #pragma unroll
-          for (int kk = 0; kk < TILE; kk += 8)
+          for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int u = 0; u < 3; u++) {
-              dmma884(acc[u][0], acc[u][1], pa[u][kk], pb[u][kk]);
-              dmma884(acc[u][2], acc[u][3], pa[u][kk + 4], pb[u][kk + 4]);
+            for (int j = 0; j < 4; j++) {
+              const int r = wm * 32 + i * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
+              *reinterpret_cast<double2*>(&blk[r * FAC_LDS + c]) = make_double2(-g.acc[i][j][0], -g.acc[i][j][1]);
             }
+          if (kc > 0) {
+            // ... and block column k-1, what the whole factorisation waits for (published by the panel task of the
+            // previous step), is applied there: the 64 x 64 tile L[k,k-1] is fetched in ONE round of loads (sixteen
+            // 16-byte loads in flight per thread, instead of four pipeline slabs issued two at a time)
+            FEVENT(0, kc, 4);
+            wait_flag(lflag + kc, kc, fa.ctl, fa.max_spins);
+            FEVENT(0, kc, 5);
+            stage_tile(sB, L + (int64_t)c0 * npad + (c0 - TILE), npad);
+            __syncthreads();
+            FEVENT(0, kc, 6);
+          }
+        } else if (kc == 0) {
+          stage_tile(blk, Akk, npad);
+          __syncthreads();
+        } else {
+          // chain link: S of the tile (k,k-1) is in sB and the partial block in blk (both parked long ago by P(b,m,k) and
+          // Dpre(b,k), fetched by cp.async behind the previous link's factorisation); T_mm is still in `tin`
+          FEVENT(0, kc, 4);
+          cp_async_wait<0>();
+          __syncthreads();
+          FEVENT(0, kc, 5);
+          double xa[8][2][2];
+          panel_product(xa, sB, tin, warp, gq, t);
+          __syncthreads();   // everyone has read S and T_mm
 #pragma unroll
-          for (int u = 0; u < 3; u++) {
-            double2 cur = *dst[u];
-            cur.x -= acc[u][0] + acc[u][2];
-            cur.y -= acc[u][1] + acc[u][3];
-            *dst[u] = cur;
+          for (int c = 0; c < 2; c++) {
+            const int jf = c ? 7 - warp : warp;
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++)
+              *reinterpret_cast<double2*>(&sB[(8 * ii + gq) * FAC_LDS + 8 * jf + 2 * t]) = make_double2(xa[ii][c][0], xa[ii][c][1]);
+          }
+          __syncthreads();
+          FEVENT(0, kc, 6);
+        }
+        if (kc > 0) {
+          // the update with block column k-1 runs on the 36 8 x 8 fragments of the lower triangle only, nine per warp (the
+          // 32 x 32 quadrant layout of the pipeline computes 48 fragments on three warps)
+          diag_update_blocked(blk, sB, warp, gq, t);
+          FPROF(2);
+        }
+        FEVENT(0, kc, 1);
+        if (tid == 0) s_bad = __ldcg(fa.info + b);
+        __syncthreads();
+        FPROF(7);
+        diag_chol_inv_blocked(blk, tin, s_dval, s_inv, &s_bad, c0, fa.prof);
+        FPROF(6);
+        FEVENT(0, kc, 2);
+        // T_kk is what the panel and inverse tasks of this step wait for: stored and published first; L_kk itself is
+        // read by no task of this kernel and follows behind the flags (chain: in front, so that its buffer is free)
+        for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
+          const int r = e >> 5, c = (e & 31) * 2;
+          *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&tin[r * FAC_LDS + c]);
+        }
+        if (tid == 0) fa.info[b] = s_bad;
+        if (chain) {
+          for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&blk[r * FAC_LDS + c]);
+          }
+          // Three flags in ONE wait (their loads in flight together, one barrier): S of the next tile parked, the next
+          // partial block parked -- both happened during the factorisation -- and P(b,k-1,k) done: lflag[k] = k + 1
+          // below also says "block row k of L is final up to column k", and the chain did not wait for that task, whose
+          // own (smaller) value of the flag must be in place first.  The barrier also says that nobody reads L_kk or
+          // the old X any more, so the next link's operands can travel while this one publishes.
+          const bool more = kc + 1 < nb;
+          if (more || kc > 0) {
+            SlabWaiter w3{more ? fa.sflag + (int64_t)b * nb + kc + 1 : lflag + kc,
+                          more ? fa.dflag + (int64_t)b * nb + kc + 1 : lflag + kc, fa.ctl, &s_known, 0, 0, fa.max_spins};
+            w3.fc = lflag + kc;
+            w3.need_c = kc;
+            w3(0);
+            if (more) {
+              stage_tile_async(sB, T + (int64_t)(c0 + TILE) * npad + c0, npad);
+              stage_tile_async(blk, L + (int64_t)(c0 + TILE) * npad + (c0 + TILE), npad);
+              cp_async_commit();
+            }
           }
         }
-        FPROF(2);
+        publish2(lflag + kc, kc + 1, tflag + kc, kc + 1);
+        FEVENT(0, kc, 3);
+        if (!chain) {
+          for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&blk[r * FAC_LDS + c]);
+          }
+        }
+        // sum of log L_ii and the diagonal-block share of beta = T z (row r of T_kk times z_k), both in a fixed order
+        if (warp == 0) {
+          double v = log(s_dval[lane]) + log(s_dval[lane + 32]);
+          v = warp_sum(v);
+          if (lane == 0) fa.fpart[((int64_t)b * nb + kc) * 2 + 1] = v;
+        } else if (tid >= 64) {
+          // z_k through s_inv (free after the factorisation; only these two warps touch it): the row sums run on
+          // shared-memory operands four ahead of the FMA chain instead of one global load per term
+          const int r = tid - 64;
+          s_inv[r] = __ldg(fa.z + (int64_t)b * npad + c0 + r);
+          asm volatile("bar.sync 1, 64;");
+          const double* trow = tin + r * FAC_LDS;
+          double acc = 0.0;
+          int c = 0;
+          for (; c + 3 <= r; c += 4) {
+            const double t0 = trow[c], t1 = trow[c + 1], t2 = trow[c + 2], t3 = trow[c + 3];
+            const double z0 = s_inv[c], z1 = s_inv[c + 1], z2 = s_inv[c + 2], z3 = s_inv[c + 3];
+            acc = fma(t0, z0, acc);
+            acc = fma(t1, z1, acc);
+            acc = fma(t2, z2, acc);
+            acc = fma(t3, z3, acc);
+          }
+          for (; c <= r; c++) acc = fma(trow[c], s_inv[c], acc);
+          fa.beta[(int64_t)b * npad + c0 + r] = acc;
+        }
+        FPROF(5);
       }
-      FEVENT(0, k, 1);
-      if (tid == 0) s_bad = __ldcg(fa.info + b);
-      __syncthreads();
-      FPROF(7);
-      diag_chol_inv_blocked(blk, tin, s_dval, s_inv, &s_bad, k0, fa.prof);
-      FPROF(6);
-      FEVENT(0, k, 2);
-      // beta = T z, diagonal-block share: row r of T_kk times z_k (fixed order; off the flags' path: after the publish)
-      // T_kk is what the panel and inverse tasks of this step wait for: stored and published first; L_kk itself is
-      // read by no task of this kernel and follows behind the flags
-      for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        *reinterpret_cast<double2*>(Tkk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&tin[r * FAC_LDS + c]);
-      }
-      if (tid == 0) fa.info[b] = s_bad;
-      // lflag[k] = k + 1 also says "block row k of L is final up to column k": with the fused panel this task did not wait
-      // for P(b,k-1,k), whose own (smaller) value of the flag must be in place before this one -- it finished long ago
-      if (fuse) wait_flag(lflag + k, k, fa.ctl, fa.max_spins);
-      publish2(lflag + k, k + 1, tflag + k, k + 1);
-      FEVENT(0, k, 3);
-      for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&blk[r * FAC_LDS + c]);
-      }
-      if (warp == 0) {   // sum of log L_ii in a fixed order
-        double v = log(s_dval[lane]) + log(s_dval[lane + 32]);
-        v = warp_sum(v);
-        if (lane == 0) fa.fpart[((int64_t)b * nb + k) * 2 + 1] = v;
-      } else if (tid >= 64) {
-        const int r = tid - 64;
-        const double* zk = fa.z + (int64_t)b * npad + k0;
-        double acc = 0.0;
-        for (int c = 0; c <= r; c++) acc = fma(tin[r * FAC_LDS + c], __ldg(zk + c), acc);
-        fa.beta[(int64_t)b * npad + k0 + r] = acc;
-      }
-      FPROF(5);
     } else if (type == 1) {
       // ---------------- P(b,k,i) ----------------
       const int i = idx, i0 = i * TILE;
@@ -759,7 +894,7 @@ __global__ void __launch_bounds__(FAC_THREADS, 3) factor_kernel(FactorArgs fa) {
           const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
           *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
         }
-      if (fa.fuse_panel && i == k + 1) {
+      if (FUSED && i == k + 1) {
         // fused-panel launches: S goes to the unused tile (i,k) of the T slab for D(b,i) (see there)
         double* Sik = T + (int64_t)i0 * npad + k0;
 #pragma unroll

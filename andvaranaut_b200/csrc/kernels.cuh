@@ -29,6 +29,7 @@ struct WsPtrs {
   int32_t* lflag;  // [B][nb]                 progress flags of the factor kernel (factor.cuh)
   int32_t* tflag;  // [B][nb]
   int32_t* sflag;  // [B][nb]                 behind ctl
+  int32_t* dflag;  // [B][nb]                 behind sflag
   int32_t* ctl;    // [8]                     ticket counter, abort flag
 };
 

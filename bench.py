@@ -174,7 +174,7 @@ def headline_config(B, world):
             'l2': 'inputs larger than L2: the working set of one step is 4.4 GiB per GPU at B=64 (126 MB L2)'}
 
 
-def traffic_from_profiles(kernel='factor_kernel', pattern='r*_ncu_factor*_b64.json'):
+def traffic_from_profiles(kernel='factor_kernel', pattern='r*_ncu_*factor*_b64*.json'):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` from the NEWEST committed `ncu --set full`
     summary of the headline workload (profiles/, written by tools/ncu_summary.py); (None, None) if there is none."""
     unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
@@ -459,7 +459,7 @@ def main():
         def step_e2e():
             return shard.loglik_grad(eng, thetas_all)
         d2h = world * B * (P + 2) * 8
-    e2e_ms = timed_host(step_e2e, args.steps)
+    e2e_ms = timed_host(step_e2e, args.steps, warm=3)   # warm-up covers the one-off capture of the host call as a CUDA graph
     e2e_value = world * B / (e2e_ms * 1e-3)
 
     # ---- per-kernel timing: the same step repeated with CUDA events around every launch (recorded by the
@@ -563,7 +563,7 @@ def per_config(per, args, torch, dist, shard, GPEngine, dev, rank, world, p64, h
     ms3 = timed(step3, steps, warm=3)
     launches3 = int(eng3.launches)
     nonpd = int((out3[0][:, 1 + P3] != 0).sum())
-    ms3_e2e = timed_host(lambda: shard.loglik_grad(eng3, t3_all) if world > 1 else eng3.loglik_grad_host(t3_all), steps)
+    ms3_e2e = timed_host(lambda: shard.loglik_grad(eng3, t3_all) if world > 1 else eng3.loglik_grad_host(t3_all), steps, warm=3)
     eng3.set_profiling(True)
     eng3.loglik_grad(t3)
     ph3 = eng3.phase_ms()
