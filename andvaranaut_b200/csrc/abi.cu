@@ -32,6 +32,7 @@ struct avn_gp {
   int device = -1;                    // CUDA device the handle is bound to (current device at avn_gp_create, or at the
                                       // first call that enqueues work when no device was visible at create time)
   bool dev_ready = false;             // shared-memory opt-ins / occupancy of this handle's kernels done on `device`
+  int sm_count = 0;                   // SMs of `device`
   int fac_resident = 0;               // CTAs of the persistent factor kernel that are resident at once on `device`
   int fac_resident_fused = 0;         // the same with the fused-panel shared-memory footprint (three tiles)
   unsigned max_spins = 1u << 26;      // bound of the factor kernel's flag waits, in polls (avn_gp_set_debug)
@@ -376,6 +377,7 @@ static int ensure_ready(avn_gp* gp) {
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, factor_kernel<false>, FAC_THREADS, FAC_SMEM_BYTES);
   if (e != cudaSuccess || per_sm < 1) return fail_cuda("factor occupancy", e);
   gp->fac_resident = sms * per_sm;
+  gp->sm_count = sms;
   int per_sm_f = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, factor_kernel<true>, FAC_THREADS, FAC_SMEM_BYTES_FUSED);
   if (e != cudaSuccess || per_sm_f < 1) return fail_cuda("factor occupancy (fused panel)", e);
@@ -395,7 +397,7 @@ static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W,
   if (gp->progs.yw.nstages > 0 && gp->progs.yw.nparams > max_np) max_np = gp->progs.yw.nparams;
   int64_t stage_doubles = max_np >= 0 ? gp->N * (1 + max_np) : 0;
   if (stage_doubles * 8 > kWarpStageMaxBytes) stage_doubles = 0;
-  warp_kernel<<<dim3((unsigned)gp->kd.d + 1, (unsigned)B), 256, (size_t)stage_doubles * 8, st>>>(
+  warp_kernel<<<dim3((unsigned)gp->kd.d + 1, (unsigned)B), WARP_THREADS, (size_t)stage_doubles * 8, st>>>(
       gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W, (int)stage_doubles);
   LAUNCH_CHECK("warp_kernel");
   scale_kernel<<<dim3((unsigned)((npad + 255) / 256), (unsigned)B), 256, 0, st>>>(gp->kd, (int)npad, theta, W);
@@ -511,7 +513,7 @@ static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, 
   }
   if (want_alpha) {
     Phase ph(gp, AVN_PH_ALPHA, st);
-    alpha_kernel<<<grid, 256, 0, st>>>(W.t, W.beta, (int)npad, W.alpha);
+    alpha_kernel<<<grid, ALPHA_THREADS, 0, st>>>(W.t, W.beta, (int)npad, W.alpha);
     LAUNCH_CHECK("alpha_kernel");
   }
   return 0;
@@ -1093,7 +1095,7 @@ extern "C" int avn_gp_append(avn_gp* gp, void* state_dev, size_t state_bytes, co
   LAUNCH_CHECK("kvec_kernel");
   beta_kernel<<<dim3((unsigned)nb, 1), 256, 0, st>>>(T, kvec, (int)npad, v, fpart);
   LAUNCH_CHECK("beta_kernel");
-  alpha_kernel<<<dim3((unsigned)nb, 1), 256, 0, st>>>(T, v, (int)npad, w);
+  alpha_kernel<<<dim3((unsigned)nb, 1), ALPHA_THREADS, 0, st>>>(T, v, (int)npad, w);
   LAUNCH_CHECK("alpha_kernel");
   append_kernel<<<nblk, 256, 0, st>>>(kd, (int)N, (int)npad, hyp, xnew_dev, znew_dev, w, mu_part, fpart, T, alpha, xs, x2,
                                       info_dev);

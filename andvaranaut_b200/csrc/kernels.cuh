@@ -38,7 +38,8 @@ constexpr int WSTAT = 16;
 // ------------------------------------------------------------------------------------------------
 // K0: conversions.  grid (d + 1, B): CTA m < d converts input column m, CTA d converts the outputs.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs, const double* __restrict__ X,
+constexpr int WARP_THREADS = 256;   // (512 threads: 85 -> 74 us at B = 1 but slower batched, and the block reductions change order)
+__global__ void __launch_bounds__(WARP_THREADS) warp_kernel(KernDesc kd, WarpProgs progs, const double* __restrict__ X,
                                                    const double* __restrict__ y, int N, int npad,
                                                    const double* __restrict__ theta, WsPtrs ws, int stage_doubles) {
   // stage_doubles >= N (1 + nparams): the column and its parameter Jacobians live in dynamic shared memory while the
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) warp_kernel(KernDesc kd, WarpProgs progs,
   // with block reductions between: on the strided global arrays each pass paid an L2 round trip per element -- 90 us of
   // a 1.1 ms evaluation at B = 1) and are written to their global layout once at the end.  Same arithmetic either way.
   extern __shared__ __align__(16) double wsm[];
-  __shared__ double sh[128];
+  __shared__ double sh[192];
   const int b = blockIdx.y, m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const double* th = theta + (int64_t)b * kd.P;
   if (m < kd.d) {
@@ -315,33 +316,39 @@ __global__ void __launch_bounds__(256, AVN_COV_MINB) cov1_kernel(KernDesc kd, in
 
 // K2 (Cholesky + triangular inverse + beta) lives in factor.cuh.
 
-// alpha = T^T beta.  grid (nb, B), 256 threads.
-__global__ void __launch_bounds__(256) alpha_kernel(const double* __restrict__ Tall, const double* __restrict__ beta_all,
-                                                    int npad, double* __restrict__ alpha_all) {
-  __shared__ double part[4][TILE];
+// alpha = T^T beta.  grid (nb, B), ALPHA_THREADS threads: 64 columns x 16 row groups (row group g takes rows j0 + g,
+// j0 + g + 16, ...), eight loads in flight per thread, the sums in a fixed order (sequential per thread, then a fixed tree
+// over the row groups): independent of B.  With 4 row groups a single evaluation (32 CTAs, 16 MB of T in L2) was bound
+// by its own load latency at 35 us.
+constexpr int ALPHA_THREADS = 1024, ALPHA_RG = ALPHA_THREADS / TILE;
+__global__ void __launch_bounds__(ALPHA_THREADS) alpha_kernel(const double* __restrict__ Tall, const double* __restrict__ beta_all,
+                                                              int npad, double* __restrict__ alpha_all) {
+  __shared__ double part[ALPHA_RG][TILE];
   const int b = blockIdx.y, j0 = blockIdx.x * TILE, tid = threadIdx.x;
   const int c = tid & 63, rg = tid >> 6;
   const double* T = Tall + (int64_t)b * npad * npad;
   const double* beta = beta_all + (int64_t)b * npad;
-  // sixteen loads in flight per thread, the sum itself in the same sequential order as a plain loop (with four in flight
-  // a single evaluation, 32 CTAs, was bound by its own L2 latency: 31 us for 16 MB)
   double acc = 0.0;
   int i = j0 + rg;
-  for (; i + 60 < npad; i += 64) {
-    double tv[16], bv[16];
+  for (; i + 7 * ALPHA_RG < npad; i += 8 * ALPHA_RG) {
+    double tv[8], bv[8];
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-      tv[u] = T[(int64_t)(i + 4 * u) * npad + j0 + c];
-      bv[u] = beta[i + 4 * u];
+    for (int u = 0; u < 8; u++) {
+      tv[u] = T[(int64_t)(i + ALPHA_RG * u) * npad + j0 + c];
+      bv[u] = beta[i + ALPHA_RG * u];
     }
 #pragma unroll
-    for (int u = 0; u < 16; u++) acc += tv[u] * bv[u];
+    for (int u = 0; u < 8; u++) acc += tv[u] * bv[u];
   }
-  for (; i < npad; i += 4) acc += T[(int64_t)i * npad + j0 + c] * beta[i];
+  for (; i < npad; i += ALPHA_RG) acc += T[(int64_t)i * npad + j0 + c] * beta[i];
   part[rg][c] = acc;
   __syncthreads();
-  if (tid < TILE)
-    alpha_all[(int64_t)b * npad + j0 + tid] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+  if (tid < TILE) {
+    double s8[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) s8[u] = part[2 * u][tid] + part[2 * u + 1][tid];
+    alpha_all[(int64_t)b * npad + j0 + tid] = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -263,7 +263,7 @@ __device__ __forceinline__ double prog_rev_const_d(const avn_warp_prog& pr, doub
 // accumulated into lsum / dlsum (to be block-reduced by the caller).
 // NOTE: val / dual / sh carry data between threads across __syncthreads(); they must NOT be
 // __restrict__ (noalias lets the compiler hoist their loads above the barrier).
-// sh: shared scratch, >= 64 + sizeof(AffineCoef)/8 + 2*(MAXWP+1) doubles.
+// sh: shared scratch, >= 128 + sizeof(AffineCoef)/8 + 2*(MAXWP+1) doubles (192 is enough); up to 32 warps per block.
 __device__ void run_warp_column(const avn_warp_prog& pr, const double* __restrict__ pvals, int N,
                                 double* val, int64_t vstride, double* dual,
                                 int64_t dstride, int track, double& lsum, double* __restrict__ dlsum,
@@ -271,9 +271,9 @@ __device__ void run_warp_column(const avn_warp_prog& pr, const double* __restric
   const int np = pr.nparams;
   const int tid = threadIdx.x, nt = blockDim.x;
   double* red = sh;                                   // 32 doubles: block_sum scratch
-  double* stat = sh + 32;                             // 32 doubles: statistics broadcast
-  AffineCoef* coef = reinterpret_cast<AffineCoef*>(sh + 64);
-  double* zero = sh + 64 + (sizeof(AffineCoef) + 7) / 8;  // running image of 0: value + np duals
+  double* stat = sh + 32;                             // 96 doubles: per-warp min / max and their indices
+  AffineCoef* coef = reinterpret_cast<AffineCoef*>(sh + 128);
+  double* zero = sh + 128 + (sizeof(AffineCoef) + 7) / 8;  // running image of 0: value + np duals
   for (int n = tid; n < N; n += nt)
     for (int q = 0; q < np; q++) dual[n * dstride + q] = 0.0;
   if (tid == 0) {
@@ -330,9 +330,9 @@ __device__ void run_warp_column(const avn_warp_prog& pr, const double* __restric
           if (hi2 > hi || (hi2 == hi && ih2 < ihi)) { hi = hi2; ihi = ih2; }
         }
         double* slo = stat;
-        double* shi = stat + 8;
-        int* silo = reinterpret_cast<int*>(stat + 16);
-        int* sihi = silo + 8;
+        double* shi = stat + 32;
+        int* silo = reinterpret_cast<int*>(stat + 64);
+        int* sihi = silo + 32;
         __syncthreads();
         if ((tid & 31) == 0) {
           slo[tid >> 5] = lo; shi[tid >> 5] = hi; silo[tid >> 5] = ilo; sihi[tid >> 5] = ihi;

@@ -34,17 +34,20 @@ class Posterior:
         """z [B,P] -> (logp [B], dlogp/dz [B,P], info [B]).  Samples whose covariance is not positive definite
         get logp = -inf and a zero gradient."""
         z = np.atleast_2d(np.asarray(z, dtype=np.float64))
+        if self.shard is None and hasattr(self.engine, 'loglik_grad_host_begin'):
+            # the device evaluates (captured graph: upload, launches, one packed download) while the host forms the
+            # Jacobian terms of the transforms and the priors: only theta itself is needed before the launch
+            token = self.engine.loglik_grad_host_begin(self.space.theta_only(z))
+            try:
+                theta, dxdz, ljac, dljac = self.space.theta_from_z(z)
+                lp, glp = self.space.prior(theta)
+            finally:
+                ll, gll, info = self.engine.loglik_grad_host_end(token)
+            return self._assemble(z, ll, gll, info, lp, glp, dxdz, ljac, dljac, jacobian)
         theta, dxdz, ljac, dljac = self.space.theta_from_z(z)
         if self.shard is not None:
             ll, gll, info = self.shard.loglik_grad(self.engine, theta)
             lp, glp = self.space.prior(theta)
-        elif hasattr(self.engine, 'loglik_grad_host_begin'):
-            # the device evaluates (captured graph: upload, launches, one packed download) while the host forms the priors
-            token = self.engine.loglik_grad_host_begin(theta)
-            try:
-                lp, glp = self.space.prior(theta)
-            finally:
-                ll, gll, info = self.engine.loglik_grad_host_end(token)
         elif hasattr(self.engine, 'loglik_grad_host'):
             ll, gll, info = self.engine.loglik_grad_host(theta)
             lp, glp = self.space.prior(theta)
@@ -54,6 +57,9 @@ class Posterior:
             if np.any(info < 0):
                 raise RuntimeError('avn_gp_loglik_grad: factorisation aborted on the device (info = -1)')
             lp, glp = self.space.prior(theta)
+        return self._assemble(z, ll, gll, info, lp, glp, dxdz, ljac, dljac, jacobian)
+
+    def _assemble(self, z, ll, gll, info, lp, glp, dxdz, ljac, dljac, jacobian):
         self.n_eval += z.shape[0]
         self.n_calls += 1
         val = ll + lp

@@ -192,6 +192,23 @@ class ParamSpace:
             dljac[..., sl] = dlj
         return theta, dxdz, ljac, dljac
 
+    def theta_only(self, z):
+        """z [.., P] -> theta [.., P]: the first output of :meth:`theta_from_z` alone (same values), for callers that launch
+        the device evaluation before they form the Jacobian terms."""
+        z = np.asarray(z, dtype=np.float64)
+        theta = np.empty_like(z)
+        with np.errstate(all='ignore'):
+            for b, sl in zip(self.blocks, self.zslices):
+                zb = z[..., sl]
+                if b.transform == 'log':
+                    theta[..., b.theta_index] = np.exp(zb)
+                elif b.transform == 'interval':
+                    lo, hi = b.args[2], b.args[3]
+                    theta[..., b.theta_index] = lo + (hi - lo) * (1.0 / (1.0 + np.exp(-zb)))
+                else:
+                    theta[..., b.theta_index] = zb
+        return theta
+
     def z_from_theta(self, theta):
         theta = np.asarray(theta, dtype=np.float64)
         z = np.empty_like(theta)
