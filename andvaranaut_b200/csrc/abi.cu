@@ -424,6 +424,27 @@ static int run_cov(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, 
     LAUNCH_CHECK("cov1_kernel");
     return 0;
   }
+  if (kd.nkern == 2 && smem <= 48 * 1024) {
+    // two-kernel folds: instantiation per pair of kinds (at most one RatQuad per model: avn_gp_create)
+#define AVN_COV2(A, B_) \
+  case (A) * 8 + (B_): cov2_kernel<A, B_><<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout); break;
+#define AVN_COV2_ROW(A) AVN_COV2(A, AVN_RBF) AVN_COV2(A, AVN_MATERN52) AVN_COV2(A, AVN_MATERN32) AVN_COV2(A, AVN_EXPONENTIAL)
+    bool done = true;
+    switch (kd.kern[0] * 8 + kd.kern[1]) {
+      AVN_COV2_ROW(AVN_RBF) AVN_COV2(AVN_RBF, AVN_RATQUAD)
+      AVN_COV2_ROW(AVN_MATERN52) AVN_COV2(AVN_MATERN52, AVN_RATQUAD)
+      AVN_COV2_ROW(AVN_MATERN32) AVN_COV2(AVN_MATERN32, AVN_RATQUAD)
+      AVN_COV2_ROW(AVN_EXPONENTIAL) AVN_COV2(AVN_EXPONENTIAL, AVN_RATQUAD)
+      AVN_COV2_ROW(AVN_RATQUAD)
+      default: done = false;
+    }
+#undef AVN_COV2_ROW
+#undef AVN_COV2
+    if (done) {
+      LAUNCH_CHECK("cov2_kernel");
+      return 0;
+    }
+  }
   cov_kernel<<<grid, 256, smem, st>>>(kd, (int)gp->N, (int)npad, theta, W.xs, W.x2, Kout);
   LAUNCH_CHECK("cov_kernel");
   return 0;

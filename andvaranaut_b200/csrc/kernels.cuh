@@ -314,6 +314,91 @@ __global__ void __launch_bounds__(256, AVN_COV_MINB) cov1_kernel(KernDesc kd, in
   }
 }
 
+// Two-kernel folds ('RBF+Matern52', 'Matern32*RatQuad', ...), both kernel kinds known at compile time: the tile and thread
+// mapping of cov1_kernel, one pass per kernel (its own scaled inputs and row norms), the fold (+ or *, warp-uniform) on
+// the 4 x 4 register block.  The generic cov_kernel runs a switch per element and kernel and spills at its 64-register
+// budget: 1.56 ms against 2 x 0.58 ms for the two single-kernel builds at N = 2000, d = 8, B = 64.
+template <int K0, int K1>
+__global__ void __launch_bounds__(256, 3) cov2_kernel(KernDesc kd, int N, int npad, const double* __restrict__ theta,
+                                                      const double* __restrict__ xs_all, const double* __restrict__ x2_all,
+                                                      double* __restrict__ Kout) {
+  extern __shared__ __align__(16) double smem[];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  int ti, tj;
+  tri_index(blockIdx.x, ti, tj);
+  const int i0 = ti * TILE, j0 = tj * TILE;
+  const int d = kd.d;
+  const double* th = theta + (int64_t)b * kd.P;
+  const double kv0 = th[kd.off_kv], kv1 = th[kd.off_kv + 1];
+  const double dadd = (kd.noise ? th[kd.off_gv] : 0.0) + kd.jitter;
+  const double alpha = kd.has_alpha ? th[kd.off_alpha] : 1.0;
+  const bool mul = kd.op[0] == AVN_MUL;
+  double* sxi = smem;                     // [2][d][64]
+  double* sxj = sxi + 2 * d * TILE;       // [2][d][64]
+  double* s2i = sxj + 2 * d * TILE;       // [2][64]
+  double* s2j = s2i + 2 * TILE;
+  for (int k = 0; k < 2; k++) {
+    const double* xs = xs_all + ((int64_t)b * 2 + k) * npad * d;
+    const double* x2 = x2_all + ((int64_t)b * 2 + k) * npad;
+    for (int e = tid; e < TILE * d; e += 256) {
+      const int r = e / d, m = e - r * d;
+      sxi[(k * d + m) * TILE + r] = xs[(int64_t)i0 * d + e];
+      sxj[(k * d + m) * TILE + r] = xs[(int64_t)j0 * d + e];
+    }
+    if (tid < TILE) s2i[k * TILE + tid] = x2[i0 + tid];
+    else if (tid < 2 * TILE) s2j[k * TILE + tid - TILE] = x2[j0 + tid - TILE];
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double out[4][4];
+  auto pass = [&](auto kind_tag, int k, double kvk) {
+    constexpr int KIND = decltype(kind_tag)::value;
+    double dot[4][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) dot[rr][cc] = 0.0;
+    for (int m = 0; m < d; m++) {
+      const double2* pi = reinterpret_cast<const double2*>(sxi + (k * d + m) * TILE + ty * 4);
+      const double2* pj = reinterpret_cast<const double2*>(sxj + (k * d + m) * TILE + tx * 4);
+      const double2 a0 = pi[0], a1 = pi[1], b0 = pj[0], b1 = pj[1];
+      const double xi[4] = {a0.x, a0.y, a1.x, a1.y}, xj[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) dot[rr][cc] = fma(xi[rr], xj[cc], dot[rr][cc]);   // sequential in m
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        double r2 = __dadd_rn(__dmul_rn(-2.0, dot[rr][cc]), __dadd_rn(s2i[k * TILE + ty * 4 + rr], s2j[k * TILE + tx * 4 + cc]));
+        r2 = r2 > 0.0 ? r2 : 0.0;
+        double kk, dk;
+        kern_val_fast<KIND, false>(r2, alpha, kk, dk);
+        const double v = __dmul_rn(kvk, kk);
+        if (k == 0) out[rr][cc] = v;
+        else out[rr][cc] = mul ? __dmul_rn(out[rr][cc], v) : __dadd_rn(out[rr][cc], v);
+      }
+  };
+  pass(std::integral_constant<int, K0>{}, 0, kv0);
+  pass(std::integral_constant<int, K1>{}, 1, kv1);
+  double* Kb = Kout + (int64_t)b * npad * npad;
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int I = i0 + ty * 4 + rr;
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      const int J = j0 + tx * 4 + cc;
+      if (I >= N || J >= N) out[rr][cc] = (I == J) ? 1.0 : 0.0;
+      else if (I == J) out[rr][cc] += dadd;
+    }
+    double2* dst = reinterpret_cast<double2*>(Kb + (int64_t)I * npad + j0 + tx * 4);
+    dst[0] = make_double2(out[rr][0], out[rr][1]);
+    dst[1] = make_double2(out[rr][2], out[rr][3]);
+  }
+}
+
 // K2 (Cholesky + triangular inverse + beta) lives in factor.cuh.
 
 // alpha = T^T beta.  grid (nb, B), ALPHA_THREADS threads: 64 columns x 16 row groups (row group g takes rows j0 + g,

@@ -124,3 +124,30 @@ def test_factorize_for_predict_matches_loglik_state():
     kv = go.kdiag_total(spec, go.unpack(spec, th)['kv'])
     assert np.max(np.abs(mu.cpu().numpy() - mu_r)) <= 1e-8 * np.max(np.abs(mu_r))
     assert np.max(np.abs(var.cpu().numpy() - var_r) / np.maximum(np.abs(var_r), kv)) <= 1e-8
+
+
+@pytest.mark.parametrize('N,B', [(40, 2), (64, 3), (100, 1), (130, 4), (449, 1), (1000, 2)])
+def test_chain_launch_equals_throughput_launch(N, B, monkeypatch):
+    """Few samples take the fused-panel instantiation of the factor kernel (one chain CTA per sample, Dpre tasks, parked
+    S tiles); many samples the throughput instantiation.  Same arithmetic: forcing either mode on the same inputs
+    (development knob AVN_FAC_FUSE, read at every launch) gives the same bits in L, T, ll and the gradient, for one
+    block row, a ragged last block row and many block rows."""
+    spec = go.ModelSpec(nx=3, kerns=['Matern52'])
+    X, y, th, _ = cases.synth(spec, N, seed=300 + N)
+    thetas = th[None, :] * np.exp(0.05 * np.random.default_rng(N).normal(size=(B, len(th))))
+    eng = engine(spec)
+    eng.set_data(X, y)
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('AVN_FAC_FUSE', mode)
+        ll, grad, info = eng.loglik_grad(thetas)
+        torch.cuda.synchronize()
+        bufs = eng.debug_buffers()
+        res[mode] = (ll.clone(), grad.clone(), info.clone(), bufs['kl'].clone(), bufs['t'].clone())
+        assert int(info.abs().sum()) == 0
+    npad = res['0'][3].shape[-1]
+    tri = torch.tril(torch.ones(npad, npad, dtype=torch.bool, device=res['0'][3].device))
+    assert torch.equal(res['0'][0], res['1'][0]) and torch.equal(res['0'][1], res['1'][1])
+    assert torch.equal(res['0'][4][:, tri], res['1'][4][:, tri])          # T: lower triangle (the upper tiles are scratch)
+    lt0, lt1 = res['0'][3][:, tri], res['1'][3][:, tri]
+    assert torch.equal(lt0, lt1)
