@@ -249,6 +249,8 @@ extern "C" int avn_gp_set_data(avn_gp* gp, const double* X_dev, const double* y_
   return 0;
 }
 
+static const int64_t kKinvSchedInts = 258 + 3 * 256;      // scheduler words of kinv_grad_fast_single_kernel (kinv_fast.cuh)
+
 static void layout(const avn_gp* gp, int64_t B, avn_ws_layout* L) {
   const KernDesc& kd = gp->kd;
   const int64_t npad = npad_of(gp->N), nb = npad / TILE, ntiles = nb * (nb + 1) / 2;
@@ -274,8 +276,9 @@ static void layout(const avn_gp* gp, int64_t B, avn_ws_layout* L) {
   L->gpart = take(B * ntiles * MAXACC);
   L->gxpart = take(gp->has_xwarp ? B * nb * npad * kd.d : 0);
   L->fpart = take(B * nb * 2);
-  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], 8 control words per stream group, sflag [B][nb], dflag [B][nb]
-  L->fflags = take((4 * B * nb + 8 * 8 + 1) / 2);
+  // int32 progress flags of the factor kernel: lflag [B][nb], tflag [B][nb], 8 control words per stream group, sflag [B][nb], dflag [B][nb],
+  // and the scheduler words of the single-sample gradient kernel (kinv_grad_fast_single_kernel)
+  L->fflags = take((4 * B * nb + 8 * 8 + kKinvSchedInts + 1) / 2);
   L->total = off;
 }
 
@@ -291,6 +294,7 @@ static WsPtrs ws_ptrs(const avn_ws_layout& L, void* ws, int64_t B) {
   p.ctl = p.tflag + B * L.nb;
   p.sflag = p.ctl + 64;
   p.dflag = p.sflag + B * L.nb;
+  p.ksched = p.dflag + B * L.nb;
   return p;
 }
 
@@ -340,7 +344,7 @@ static size_t kxs_smem_bytes(const KernDesc& kd) { return (size_t)(kd.nkern * TI
 static size_t predict_grad_smem_bytes(const KernDesc& kd) { return kxs_smem_bytes(kd) + (size_t)(4 * TILE * 2 * kd.d) * 8; }
 
 static int launch_kinv_fast(bool optin_only, int kind, bool gx, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd,
-                            int N, int npad, const double* theta, const WsPtrs& W);
+                            int N, int npad, const double* theta, const WsPtrs& W, int single = 0, int nsm = 0);
 
 // Once per handle, on the handle's device (the caller holds a DevGuard): every shared-memory opt-in this model's
 // kernels need and the resident CTA count of the persistent factor kernel.  cudaFuncSetAttribute is per device, so the
@@ -541,7 +545,7 @@ static int run_beta_alpha(avn_gp* gp, int64_t B, const WsPtrs& W, int64_t npad, 
 }
 
 static cudaError_t zero_flags(const WsPtrs& W, int64_t B, int64_t nb, cudaStream_t st) {
-  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(4 * B * nb + 64), st);
+  return cudaMemsetAsync(W.lflag, 0, sizeof(int32_t) * (size_t)(4 * B * nb + 64 + kKinvSchedInts), st);
 }
 
 extern "C" int avn_gp_cov(avn_gp* gp, const double* theta_dev, int64_t B, double* K_dev, void* ws_dev, size_t ws_bytes,
@@ -587,13 +591,21 @@ static WsPtrs ws_offset(const WsPtrs& W, const avn_gp* gp, const avn_ws_layout& 
   return p;
 }
 
-// optin_only: the shared-memory opt-in of this instantiation (ensure_ready), no launch
+// optin_only: the shared-memory opt-in of this instantiation (ensure_ready), no launch.  single > 0: the single-sample
+// kernel on `single` CTAs (as many as are resident at once), tiles dealt by placement.
 template <int KIND, bool GX>
 static int launch_kinv_fast_t(bool optin_only, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd, int N, int npad,
-                              const double* theta, const WsPtrs& W) {
+                              const double* theta, const WsPtrs& W, int single, int nsm) {
   if (optin_only) {
     cudaError_t e = opt_in_smem(kinv_grad_fast_kernel<KIND, GX>, smem);
+    if (e == cudaSuccess) e = opt_in_smem(kinv_grad_fast_single_kernel<KIND, GX>, smem);
     if (e != cudaSuccess) return fail_cuda("kinv_grad_fast smem opt-in", e);
+    return 0;
+  }
+  if (single > 0) {
+    const int ntiles = (int)grid.x;
+    kinv_grad_fast_single_kernel<KIND, GX><<<(unsigned)(ntiles < single ? ntiles : single), KinvG2::NTHREADS, smem, st>>>(
+        kd, N, npad, theta, W.t, W.alpha, W.xw, W.xs, W.x2, W.gpart, W.gxpart, ntiles, nsm, W.ksched);
     return 0;
   }
   kinv_grad_fast_kernel<KIND, GX><<<grid, KinvG2::NTHREADS, smem, st>>>(kd, N, npad, theta, W.t, W.alpha, W.xw, W.xs, W.x2,
@@ -602,11 +614,11 @@ static int launch_kinv_fast_t(bool optin_only, dim3 grid, size_t smem, cudaStrea
 }
 
 static int launch_kinv_fast(bool optin_only, int kind, bool gx, dim3 grid, size_t smem, cudaStream_t st, const KernDesc& kd,
-                            int N, int npad, const double* theta, const WsPtrs& W) {
-#define AVN_DISPATCH(K)                                                                           \
-  case K:                                                                                         \
-    return gx ? launch_kinv_fast_t<K, true>(optin_only, grid, smem, st, kd, N, npad, theta, W)    \
-              : launch_kinv_fast_t<K, false>(optin_only, grid, smem, st, kd, N, npad, theta, W);
+                            int N, int npad, const double* theta, const WsPtrs& W, int single, int nsm) {
+#define AVN_DISPATCH(K)                                                                                        \
+  case K:                                                                                                      \
+    return gx ? launch_kinv_fast_t<K, true>(optin_only, grid, smem, st, kd, N, npad, theta, W, single, nsm)    \
+              : launch_kinv_fast_t<K, false>(optin_only, grid, smem, st, kd, N, npad, theta, W, single, nsm);
   switch (kind) {
     AVN_DISPATCH(AVN_RBF)
     AVN_DISPATCH(AVN_MATERN52)
@@ -620,7 +632,7 @@ static int launch_kinv_fast(bool optin_only, int kind, bool gx, dim3 grid, size_
 
 // the whole evaluation for samples [b0, b0+Bg) on one stream
 static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll, double* grad, int32_t* info,
-                        const WsPtrs& W, const avn_ws_layout& L, cudaStream_t st) {
+                        const WsPtrs& W, const avn_ws_layout& L, cudaStream_t st, bool single_sample = false) {
   const KernDesc& kd = gp->kd;
   const int64_t npad = L.npad, nb = L.nb, ntiles = nb * (nb + 1) / 2;
   const bool want_grad = grad != nullptr;
@@ -639,8 +651,9 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
     const dim3 grid((unsigned)ntiles, (unsigned)Bg);
     if (kd.nkern == 1) {
       // single-kernel model: DMMA epilogue specialised on the kernel kind
+      // a single sample (the call's B, not a group's): tiles dealt by placement over the resident CTAs (kinv_fast.cuh)
       rc = launch_kinv_fast(false, kd.kern[0], gp->has_xwarp, grid, kinv_fast_smem_bytes(kd), st, kd, (int)gp->N, (int)npad,
-                            theta, W);
+                            theta, W, single_sample ? 3 * gp->sm_count : 0, gp->sm_count);
       if (rc) return rc;
     } else if (kd.nkern == 2 && !(kd.kern[0] == AVN_RATQUAD && kd.kern[1] == AVN_RATQUAD)) {
       // two-kernel sum / product: DMMA epilogue with the fold's product rule (kinv_fold.cuh)
@@ -706,7 +719,7 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
     cudaError_t e = zero_flags(W, B, L.nb, st);
     if (e != cudaSuccess) return fail_cuda("memset flags", e);
   }
-  if (G <= 1) return loglik_group(gp, theta_dev, B, ll_dev, grad_dev, info_dev, W, L, st);
+  if (G <= 1) return loglik_group(gp, theta_dev, B, ll_dev, grad_dev, info_dev, W, L, st, B == 1);
   for (int g = 0; g < G; g++)
     if (!gp->gstream[g]) {
       cudaError_t e = cudaStreamCreateWithFlags(&gp->gstream[g], cudaStreamNonBlocking);
@@ -792,7 +805,7 @@ extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int
     e = cudaMemcpyAsync(theta_dev, theta_host, (size_t)(B * P * 8), cudaMemcpyHostToDevice, hs);
     if (e == cudaSuccess) e = cudaMemsetAsync(info_dev, 0, (size_t)(B * 8), hs);   // whole [B] doubles slot of the int32 info
     if (e == cudaSuccess) e = zero_flags(W, B, L.nb, hs);
-    if (e == cudaSuccess) rc = loglik_group(gp, theta_dev, B, ll_dev, want_grad ? grad_dev : nullptr, info_dev, W, L, hs);
+    if (e == cudaSuccess) rc = loglik_group(gp, theta_dev, B, ll_dev, want_grad ? grad_dev : nullptr, info_dev, W, L, hs, B == 1);
     if (e == cudaSuccess && rc == 0)
       e = cudaMemcpyAsync(out_host, packed, (size_t)(B * (P + 2) * 8), cudaMemcpyDeviceToHost, hs);
     cudaGraph_t graph = nullptr;

@@ -30,6 +30,7 @@ struct WsPtrs {
   int32_t* tflag;  // [B][nb]
   int32_t* sflag;  // [B][nb]                 behind ctl
   int32_t* dflag;  // [B][nb]                 behind sflag
+  int32_t* ksched; // scheduler words of kinv_grad_fast_single_kernel (behind dflag; zeroed with the flags)
   int32_t* ctl;    // [8]                     ticket counter, abort flag
 };
 

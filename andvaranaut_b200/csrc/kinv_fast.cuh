@@ -40,19 +40,20 @@ struct KinvFastLayout {
 #endif
 using KinvG2 = TileGemm<64, 64, AVN_KINV_BK, 32, 32, AVN_KINV_STAGES, true, true>;
 
+// one tile (ti, tj) of sample b: everything described above.  smem: the CTA's dynamic shared memory; hyp / wpart: its
+// static scratch.  Called once per CTA by the grid kernel and in a loop by the single-sample kernel.
 template <int KIND, bool WITH_GX>
-__global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
-    KernDesc kd, int N, int npad, const double* __restrict__ theta, const double* __restrict__ Tall,
-    const double* __restrict__ alpha_all, const double* __restrict__ xw_all, const double* __restrict__ xs_all,
-    const double* __restrict__ x2_all, double* __restrict__ gpart, double* __restrict__ gxpart) {
+__device__ __forceinline__ void kinv_fast_tile(const KernDesc& kd, int N, int npad, const double* __restrict__ theta,
+                                               const double* __restrict__ Tall, const double* __restrict__ alpha_all,
+                                               const double* __restrict__ xw_all, const double* __restrict__ xs_all,
+                                               const double* __restrict__ x2_all, double* __restrict__ gpart,
+                                               double* __restrict__ gxpart, int b, int tile, int ntiles_all, double* smem,
+                                               HypS& hyp, double (&wpart)[4][MAXACC]) {
   using G = KinvG2;
   constexpr int LDW = TILE + SPAD;
-  extern __shared__ double smem[];
-  __shared__ HypS hyp;
-  __shared__ double wpart[4][MAXACC];
-  const int b = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   int ti, tj;
-  tri_index(blockIdx.x, ti, tj);
+  tri_index(tile, ti, tj);
   const int i0 = ti * TILE, j0 = tj * TILE;
   const int d = kd.d;
   const double* T = Tall + (int64_t)b * npad * npad;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
   G g;
   g.zero();
   // the wm = 1 warps skip half of the first slab: alternate which hardware warps (SM sub-partitions) those are
-  const int swz = (int)((blockIdx.x * 2654435761u) >> 16) & 1;   // a function of the tile only: batch-size independent results
+  const int swz = (int)(((unsigned)tile * 2654435761u) >> 16) & 1;   // a function of the tile only: batch-size independent results
   g.swz = swz;
   // rows >= N of T are those of the identity: the k range stops at N rounded up to the slab depth, and the
   // padding rows of the last block row issue no DMMA
@@ -239,9 +240,86 @@ __global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
   }
   __syncthreads();
   const int nacc = d + 3;
-  const int64_t ntiles = gridDim.x;
-  double* gp = gpart + ((int64_t)b * ntiles + blockIdx.x) * MAXACC;
+  const int64_t ntiles = ntiles_all;
+  double* gp = gpart + ((int64_t)b * ntiles + tile) * MAXACC;
   for (int e = tid; e < nacc; e += G::NTHREADS) gp[e] = (wpart[0][e] + wpart[1][e]) + (wpart[2][e] + wpart[3][e]);
+}
+
+// grid (ntiles_lower, B): one tile per CTA, tiles numbered longest first
+template <int KIND, bool WITH_GX>
+__global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_kernel(
+    KernDesc kd, int N, int npad, const double* __restrict__ theta, const double* __restrict__ Tall,
+    const double* __restrict__ alpha_all, const double* __restrict__ xw_all, const double* __restrict__ xs_all,
+    const double* __restrict__ x2_all, double* __restrict__ gpart, double* __restrict__ gxpart) {
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  __shared__ double wpart[4][MAXACC];
+  kinv_fast_tile<KIND, WITH_GX>(kd, N, npad, theta, Tall, alpha_all, xw_all, xs_all, x2_all, gpart, gxpart, blockIdx.y,
+                                blockIdx.x, gridDim.x, smem, hyp, wpart);
+}
+
+// ONE sample (the latency path): a little more than one wave of tiles, whose lengths run from nb slabs down to 1.  The
+// hardware deals consecutive CTAs to the SMs in a pattern of its own (blocks 0, 70 and 134 share an SM on this part: 70
+// slabs on that SM against 40 on average -- the kernel took 174 us where the work is worth 110), so here a CTA takes its
+// first tile by WHERE it runs: slot s = 0, 1, 2 of SM m (a counter per SM) gets tile m of round 0 walked forwards and of
+// the later rounds walked backwards, which gives every SM about the same number of slabs (44 .. 41 at nb = 32); whatever
+// is left (the shortest tiles) is handed out through one counter as CTAs finish.  A claim word per tile (atomicCAS)
+// makes every tile run exactly once whatever the placement does.  Results are indexed by tile: same bits.
+// sched: [0] tail counter, [1 .. 256] per-SM slot counters, [257] claimed tiles of the first wave, [258 ...] claim words of
+// the first wave -- zeroed by the host.
+template <int KIND, bool WITH_GX>
+__global__ void __launch_bounds__(KinvG2::NTHREADS, 3) kinv_grad_fast_single_kernel(
+    KernDesc kd, int N, int npad, const double* __restrict__ theta, const double* __restrict__ Tall,
+    const double* __restrict__ alpha_all, const double* __restrict__ xw_all, const double* __restrict__ xs_all,
+    const double* __restrict__ x2_all, double* __restrict__ gpart, double* __restrict__ gxpart, int ntiles, int nsm,
+    int32_t* __restrict__ sched) {
+  extern __shared__ double smem[];
+  __shared__ HypS hyp;
+  __shared__ double wpart[4][MAXACC];
+  __shared__ int s_tile;
+  int32_t* claimed = sched + 258;
+  const int wave = min(ntiles, (int)gridDim.x);   // tiles dealt by placement; the rest through the tail counter
+  bool first = true;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int tile = -1;
+      if (first) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int bin = (int)(smid % (unsigned)nsm);
+        const int slot = atomicAdd(sched + 1 + (bin & 255), 1);
+        const int base = slot * nsm, cnt = min(nsm, wave - base);
+        if (bin < cnt) {
+          const int t = slot == 0 ? bin : base + cnt - 1 - bin;
+          if (atomicCAS(claimed + t, 0, 1) == 0) {
+            tile = t;
+            atomicAdd(sched + 257, 1);
+          }
+        }
+      }
+      if (tile < 0) {
+        const int c = wave + atomicAdd(sched, 1);
+        if (c < ntiles) tile = c;
+      }
+      if (tile < 0 && *reinterpret_cast<volatile int32_t*>(sched + 257) < wave) {
+        // insurance: a tile of the first wave that nobody claimed (an SM numbering or placement other than the expected
+        // one, or a CTA that has not started yet -- it will find its word taken and go to the tail counter)
+        for (int t = 0; t < wave && tile < 0; t++)
+          if (*reinterpret_cast<volatile int32_t*>(claimed + t) == 0 && atomicCAS(claimed + t, 0, 1) == 0) {
+            tile = t;
+            atomicAdd(sched + 257, 1);
+          }
+      }
+      s_tile = tile;
+    }
+    first = false;
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile < 0) break;
+    kinv_fast_tile<KIND, WITH_GX>(kd, N, npad, theta, Tall, alpha_all, xw_all, xs_all, x2_all, gpart, gxpart, 0, tile, ntiles,
+                                  smem, hyp, wpart);
+    __syncthreads();
+  }
 }
 
 }  // namespace avn
