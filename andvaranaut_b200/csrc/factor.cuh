@@ -24,25 +24,33 @@
 
 namespace avn {
 
+// Pipeline shape per launch kind.  Throughput launches: 32-deep slabs x 2 stages (72 KB, still 3 CTAs per SM) -- half the
+// per-slab barriers of 16 x 3; measured at HEAD of round 2: factor 11.88 -> 11.69 ms at c2 / B=64, 13.61 -> 13.48 ms at
+// c3 (the plain tile GEMM: 34.4 -> 35.2 TF).  Chain launches (few samples) keep 16 x 3: the tasks next to the chain wait
+// slab by slab, and finer slabs let them start sooner (factor 0.584 ms against 0.621 ms at B = 1).
 #ifndef AVN_FAC_BK
-#define AVN_FAC_BK 16
-#define AVN_FAC_STAGES 3
+#define AVN_FAC_BK 32
+#define AVN_FAC_STAGES 2
 #endif
-constexpr int FAC_BK = AVN_FAC_BK, FAC_STAGES = AVN_FAC_STAGES;
-constexpr int FAC_SPB = TILE / FAC_BK;   // pipeline stages per 64-deep block
-using FacKK = TileGemm<64, 64, FAC_BK, 32, 32, FAC_STAGES, false, false>;
-using FacKR = TileGemm<64, 64, FAC_BK, 32, 32, FAC_STAGES, false, true>;
-constexpr int FAC_THREADS = 128;
 #ifndef AVN_POLL_NS
 #define AVN_POLL_NS 64      // pause between two polls of a progress flag (measured: see DESIGN.md)
 #endif
+constexpr int FAC_THREADS = 128;
 constexpr int FAC_LDS = TILE + SPAD;                                 // 68: conflict-free fragment loads both ways
 constexpr size_t cmax(size_t a, size_t b) { return a > b ? a : b; }
-// two staged 64 x 64 tiles for the epilogues alias the pipeline buffers
-constexpr size_t FAC_SMEM_BYTES = cmax((size_t)2 * TILE * FAC_LDS * 8, cmax(FacKK::SMEM_BYTES, FacKR::SMEM_BYTES));
-// fused-panel launches (few samples): a third staged tile behind the first two
-constexpr size_t FAC_SMEM_BYTES_FUSED = (size_t)3 * TILE * FAC_LDS * 8;
-static_assert(FAC_SMEM_BYTES == (size_t)2 * TILE * FAC_LDS * 8, "the third tile must lie behind the pipeline buffers");
+template <bool FUSED>
+struct FacCfg {
+  static constexpr int BK = FUSED ? 16 : AVN_FAC_BK, STAGES = FUSED ? 3 : AVN_FAC_STAGES;
+  static constexpr int SPB = TILE / BK;   // pipeline slabs per 64-deep block
+  using KK = TileGemm<64, 64, BK, 32, 32, STAGES, false, false>;
+  using KR = TileGemm<64, 64, BK, 32, 32, STAGES, false, true>;
+  // two staged 64 x 64 tiles for the epilogues alias the pipeline buffers
+  static constexpr size_t SMEM2 = cmax((size_t)2 * TILE * FAC_LDS * 8, cmax(KK::SMEM_BYTES, KR::SMEM_BYTES));
+};
+constexpr size_t FAC_SMEM_BYTES = FacCfg<false>::SMEM2;
+// fused-panel launches (few samples): a third staged tile behind the first two and behind the pipeline buffers
+constexpr int FAC_THIRD_OFF = (int)(FacCfg<true>::SMEM2 / 8);   // in doubles
+constexpr size_t FAC_SMEM_BYTES_FUSED = FacCfg<true>::SMEM2 + (size_t)TILE * FAC_LDS * 8;
 
 #ifdef AVN_FACTOR_PROF
 // timeline of the critical chain (B = 1): thread 0 logs (task type, k, event, globaltimer ns) for the diagonal tasks
@@ -128,7 +136,7 @@ __device__ __forceinline__ void wait_flag(const int32_t* flag, int need, int32_t
   __syncthreads();
 }
 
-// Slab-wise operand wait inside TileGemm::run: k-slab kt belongs to the 64-deep block m = m0 + kt / FAC_SPB, which
+// Slab-wise operand wait inside TileGemm::run: k-slab kt belongs to the 64-deep block m = m0 + kt / spb, which
 // needs both progress flags >= m + 1.  `known` caches the smaller flag value seen last, so the flags are only
 // read again (thread 0, then one barrier) when the product runs ahead of what was known to be final.
 struct SlabWaiter {
@@ -140,9 +148,10 @@ struct SlabWaiter {
   unsigned max_spins;
   const int32_t* fc = nullptr;   // optional third flag with its own threshold (the chain's combined wait)
   int need_c = 0;
+  int spb = 1;                   // pipeline slabs per 64-deep block (FacCfg::SPB)
   __device__ __forceinline__ void operator()(int kt) {
-    if (kt % FAC_SPB) return;
-    const int need = m0 + kt / FAC_SPB + 1;
+    if (kt % spb) return;
+    const int need = m0 + kt / spb + 1;
     if (need <= known) return;
     if (threadIdx.x == 0) {
       unsigned spins = 0;
@@ -646,6 +655,9 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
   __shared__ int s_bad;
   __shared__ __align__(16) double s_dval[TILE];
   __shared__ __align__(16) double s_inv[TILE];
+  using FacKK = typename FacCfg<FUSED>::KK;
+  using FacKR = typename FacCfg<FUSED>::KR;
+  constexpr int FAC_BK = FacCfg<FUSED>::BK, FAC_SPB = FacCfg<FUSED>::SPB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % 2, wn = warp / 2, gq = lane >> 2, t = lane & 3;
   const int npad = fa.npad, nb = fa.nb, B = fa.B;
@@ -688,7 +700,9 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       {
         const int dpos_ = (s < nb - 1) ? ((1 + fa.dgap < nb - 1) ? 1 + fa.dgap : nb - 1) : -1;
         const int head = (dpos_ + 1) * B;           // tickets of the sample-fastest head of the list
-        if (rem < head) {
+        if (FUSED || rem < head) {
+          // (chain launches stay sample-fastest throughout: with a handful of samples the steps of all of them should
+          // advance together, and everything fits L2 anyway -- factor 1.79 ms against 1.90 ms at c2 / B = 8)
           q = rem / B;
           b = rem - q * B;
         } else {
@@ -727,7 +741,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       load_neg_tile(g.acc, Akk, npad, wm, wn, gq, t);
       if (k > 1) {
         const bool idle_quadrant = (wm == 0 && wn == 1);
-        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins};
+        SlabWaiter w{lflag + k, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins, nullptr, 0, FAC_SPB};
         g.run(smem, L + (int64_t)k0 * npad, npad, rows_k, L + (int64_t)k0 * npad, npad, 64, k0 - TILE,
               [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
       }
@@ -752,7 +766,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       // still finishes the tile for everybody else; products and update are the same code on the same operands as in
       // throughput launches, so both modes give the same bits.  Such launches carry a third 64 x 64 tile of shared memory.
       constexpr bool chain = FUSED;
-      double* blk = chain ? smem + 2 * TILE * FAC_LDS : sA;   // the diagonal block: A_kk updated, then L_kk
+      double* blk = chain ? smem + FAC_THIRD_OFF : sA;   // the diagonal block: A_kk updated, then L_kk
       double* tin = chain ? sA : sB;                          // receives T_kk
       const int k_end = chain ? nb : k + 1;
       for (int kc = k; kc < k_end; kc++) {
@@ -768,7 +782,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
             // only the lower triangle of the block is used: the warp of the upper-right quadrant computes nothing;
             // block columns 0 .. k-2 of row k through the pipeline: final long before this task is on the critical path
             const bool idle_quadrant = (wm == 0 && wn == 1);
-            SlabWaiter w{lflag + kc, lflag + kc, fa.ctl, &s_known, 0, 0, fa.max_spins};
+            SlabWaiter w{lflag + kc, lflag + kc, fa.ctl, &s_known, 0, 0, fa.max_spins, nullptr, 0, FAC_SPB};
             g.run(smem, L + (int64_t)c0 * npad, npad, rows_c, L + (int64_t)c0 * npad, npad, 64, c0 - TILE,
                   [&](int kt) { w(kt); }, idle_quadrant ? 0x7fffffff : 0);
           }
@@ -901,7 +915,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       FacKK g;
       load_neg_tile(g.acc, Aik, npad, wm, wn, gq, t);
       if (k > 0) {
-        SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins};
+        SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins, nullptr, 0, FAC_SPB};
         g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
               [&](int kt) { w(kt); });
         FPROF(2);
@@ -955,7 +969,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       const int j = idx, j0 = j * TILE;
       FacKR g;
       g.zero();
-      SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0, fa.max_spins};
+      SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0, fa.max_spins, nullptr, 0, FAC_SPB};
       // first slab: B = T[j,j] is lower triangular, its columns n >= 32 vanish for the first 32 k
       g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
             [&](int kt) { w(kt); }, wn == 1 ? 32 / FAC_BK : 0);
