@@ -936,14 +936,14 @@ static void launch_kxs(const KernDesc& kd, dim3 grid, cudaStream_t st, int N, in
                                                      ns, mu_part);
 }
 
-static const int64_t kPanelCols = 148 * 64 * 2;  // test points per K_xs panel
+static const int64_t kPanelCols = 148 * 64 * AVN_PRED_CTAS;  // test points per K_xs panel: one wave of the predict kernels
 
 // Small test batches (BO candidates, refine / inverse-problem starts): fewer 64-point column blocks than CTA slots
 // (2 resident CTAs x 148 SMs).  The training rows are then split over blockIdx.y as well -- as many splits as still fit
 // in ONE wave (a second, partly filled wave costs more than it gains: measured) -- and a finish kernel sums the partials
 // in fixed order.  A function of the TOTAL M, so that the result does not depend on how a call is cut into panels.
 static int row_split(int64_t M, int64_t npad) {
-  const int64_t nblk = (M + TILE - 1) / TILE, nb = npad / TILE, slots = 2 * 148;
+  const int64_t nblk = (M + TILE - 1) / TILE, nb = npad / TILE, slots = AVN_PRED_CTAS * 148;
   int64_t ns = slots / nblk;
   if (ns > nb) ns = nb;
   return (int)(ns < 1 ? 1 : ns);

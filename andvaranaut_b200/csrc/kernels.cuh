@@ -1009,7 +1009,12 @@ __global__ void __launch_bounds__(256) predict_finish_kernel(KernDesc kd, const 
   var_out[mg] = var;
 }
 
-using PredG = TileGemm<64, 64, 16, 32, 32, 4, false, true>;
+#ifndef AVN_PRED_BK
+#define AVN_PRED_BK 16
+#define AVN_PRED_STAGES 4
+#define AVN_PRED_CTAS 2      // resident CTAs per SM the panel width and the row split are sized for
+#endif
+using PredG = TileGemm<64, 64, AVN_PRED_BK, 32, 32, AVN_PRED_STAGES, false, true>;
 
 __global__ void __launch_bounds__(PredG::NTHREADS) predict_var_kernel(KernDesc kd, int npad,
                                                                       const HypS* __restrict__ hyp_g,
