@@ -653,7 +653,8 @@ static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll,
       // single-kernel model: DMMA epilogue specialised on the kernel kind
       // a single sample (the call's B, not a group's): tiles dealt by placement over the resident CTAs (kinv_fast.cuh)
       rc = launch_kinv_fast(false, kd.kern[0], gp->has_xwarp, grid, kinv_fast_smem_bytes(kd), st, kd, (int)gp->N, (int)npad,
-                            theta, W, single_sample ? 3 * gp->sm_count : 0, gp->sm_count);
+                            theta, W, single_sample ? 3 * (gp->sm_count < 256 ? gp->sm_count : 256) : 0,
+                            gp->sm_count < 256 ? gp->sm_count : 256);   // (the scheduler block holds 256 SM counters, 768 claim words)
       if (rc) return rc;
     } else if (kd.nkern == 2 && !(kd.kern[0] == AVN_RATQUAD && kd.kern[1] == AVN_RATQUAD)) {
       // two-kernel sum / product: DMMA epilogue with the fold's product rule (kinv_fold.cuh)

@@ -90,7 +90,10 @@ typedef struct {
   avn_warp_prog ywarp;             /* learnable output warp (cwgp=True) */
 } avn_model_desc;
 
-/* byte offsets of the named buffers inside a loglik workspace (for tests and profiling) */
+/* byte offsets of the named buffers inside a loglik workspace (for tests and profiling).
+ * fflags: the int32 progress words of the factor kernel -- lflag [B][nb], tflag [B][nb], 64 control words, sflag [B][nb],
+ * dflag [B][nb] (the last two only used by launches with few samples) -- followed by the 1026 scheduler words of the
+ * single-sample gradient kernel; zeroed by one memset at the start of every call. */
 typedef struct {
   int64_t npad, nb;
   int64_t xw, dxw, xs, x2, z, dz, wstat, kl, t, beta, alpha, gpart, gxpart, fpart, fflags, total;
