@@ -629,7 +629,8 @@ __device__ __forceinline__ void panel_product(double (&xa)[8][2][2], const doubl
                                               int t) {
   // (a variant that shared the S fragments between the two columns and loaded the operands of step k + 4 before the
   // DMMAs of step k was slower both in the 168-register kernel -- 3.9 us against 2.3 us per chain link, +2 % on throughput
-  // launches -- and as a chain-only instantiation with 248 registers: factor 0.584 -> 0.64 ms at B = 1)
+  // launches -- and as a chain-only instantiation with 248 registers: factor 0.584 -> 0.64 ms at B = 1; a layout with
+  // row fragments 2w, 2w+1 x all eight column fragments per warp -- 104 operand loads instead of 162 -- changed nothing)
 #pragma unroll
   for (int ii = 0; ii < 8; ii++) xa[ii][0][0] = xa[ii][0][1] = xa[ii][1][0] = xa[ii][1][1] = 0.0;
 #pragma unroll
