@@ -16,8 +16,9 @@
 // factorisation (the previous version needed 3 launches per block column).
 //
 // Flags (int32, zeroed by the host before the launch):
-//   lflag[b][i] = number of final 64-wide block columns in block row i of L   (D(b,k) also publishes T[k,k])
-//   tflag[b][j] = number of final block rows in block column j of T, counted as (row index + 1)
+//   lflag[b][i] = number of final 64-wide block columns in block row i of L
+//   tflag[b][j] = number of final block rows in block column j of T, counted as (row index + 1): tflag[k] = k + 1, published
+//                 by the diagonal task, says that T[k,k] is there -- what the panel and inverse tasks of step k wait for
 #pragma once
 #include "avn_dev.cuh"
 #include "tile_gemm.cuh"
@@ -850,30 +851,28 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
         }
         if (tid == 0) fa.info[b] = s_bad;
         if (chain) {
+          // T_kk out first (tflag[k] = k + 1 is what its consumers wait for; nothing in this kernel reads L_kk): the tasks it
+          // feeds -- P(b,k,k+2), then Dpre(b,k+2) and the parked S of the link after next -- form a second chain of ~13 us
+          // per step with little slack against this one
+          publish(tflag + kc, kc + 1);
           for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
             const int r = e >> 5, c = (e & 31) * 2;
             *reinterpret_cast<double2*>(Akk + (int64_t)r * npad + c) = *reinterpret_cast<const double2*>(&blk[r * FAC_LDS + c]);
           }
-          // Three flags in ONE wait (their loads in flight together, one barrier): S of the next tile parked, the next
-          // partial block parked -- both happened during the factorisation -- and P(b,k-1,k) done: lflag[k] = k + 1
-          // below also says "block row k of L is final up to column k", and the chain did not wait for that task, whose
-          // own (smaller) value of the flag must be in place first.  The barrier also says that nobody reads L_kk or
-          // the old X any more, so the next link's operands can travel while this one publishes.
-          const bool more = kc + 1 < nb;
-          if (more || kc > 0) {
-            SlabWaiter w3{more ? fa.sflag + (int64_t)b * nb + kc + 1 : lflag + kc,
-                          more ? fa.dflag + (int64_t)b * nb + kc + 1 : lflag + kc, fa.ctl, &s_known, 0, 0, fa.max_spins};
-            w3.fc = lflag + kc;
-            w3.need_c = kc;
+          // Two flags in ONE wait (their loads in flight together, one barrier): S of the next tile parked, the next partial
+          // block parked -- both happened during the factorisation.  The barrier also says that nobody reads L_kk or the
+          // old X any more, so the next link's operands can travel now.
+          if (kc + 1 < nb) {
+            SlabWaiter w3{fa.sflag + (int64_t)b * nb + kc + 1, fa.dflag + (int64_t)b * nb + kc + 1, fa.ctl, &s_known, 0, 0,
+                          fa.max_spins};
             w3(0);
-            if (more) {
-              stage_tile_async(sB, T + (int64_t)(c0 + TILE) * npad + c0, npad);
-              stage_tile_async(blk, L + (int64_t)(c0 + TILE) * npad + (c0 + TILE), npad);
-              cp_async_commit();
-            }
+            stage_tile_async(sB, T + (int64_t)(c0 + TILE) * npad + c0, npad);
+            stage_tile_async(blk, L + (int64_t)(c0 + TILE) * npad + (c0 + TILE), npad);
+            cp_async_commit();
           }
+        } else {
+          publish2(lflag + kc, kc + 1, tflag + kc, kc + 1);
         }
-        publish2(lflag + kc, kc + 1, tflag + kc, kc + 1);
         FEVENT(0, kc, 3);
         if (!chain) {
           for (int e = tid; e < TILE * TILE / 2; e += FAC_THREADS) {
@@ -942,7 +941,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       }
       FPROF(4);
       if (i == k + 1) FEVENT(1, k, 1);
-      wait_flag(lflag + k, k + 1, fa.ctl, fa.max_spins);   // T[k,k] is there (also orders the sA writes)
+      wait_flag(tflag + k, k + 1, fa.ctl, fa.max_spins);   // T[k,k] is there (also orders the sA writes)
       FPROF(3);
       if (i == k + 1) FEVENT(1, k, 2);
       stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
@@ -983,7 +982,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
           *reinterpret_cast<double2*>(&sB[r * FAC_LDS + c]) = make_double2(g.acc[ii][jj][0], g.acc[ii][jj][1]);
         }
       FPROF(4);
-      wait_flag(lflag + k, k + 1, fa.ctl, fa.max_spins);
+      wait_flag(tflag + k, k + 1, fa.ctl, fa.max_spins);
       FPROF(3);
       stage_tile(sA, T + (int64_t)k0 * npad + k0, npad);
       __syncthreads();
