@@ -125,8 +125,7 @@ def test_golden_next_rows(name):
     assert np.max(np.abs(m - g['pg_mu'])) <= 1e-8 * np.max(np.abs(g['pg_mu']))
     assert np.max(np.abs(v - g['pg_var'])) <= 1e-8 * max(np.max(np.abs(g['pg_var'])), kv)
     assert np.max(np.abs(dm - g['pg_dmu'])) <= 1e-8 * np.max(np.abs(g['pg_dmu']))
-    tol = 1e-6 if 'Exponential' in spec.kerns else 1e-8
-    assert np.max(np.abs(dv - g['pg_dvar'])) <= tol * max(np.max(np.abs(g['pg_dvar'])), kv)
+    assert np.max(np.abs(dv - g['pg_dvar'])) <= 1e-8 * max(np.max(np.abs(g['pg_dvar'])), kv)
     # inverse problem: engine with the reference's diagonal (sqrt(gv + jitter), no jitter), constant = training ll
     args = cases.engine_args(spec)
     args.update(noise=True, jitter=0.0)
@@ -182,8 +181,11 @@ def test_shapes_kernels_warps(name):
         # autodiff yields NaN otherwise, as do the oracle and the kernel)
         th[spec.offsets()['cw']] = 0.15
     thetas = np.stack([th, th * np.exp(0.05 * rng.normal(size=th.shape))])
-    # the Exponential kernel's diagonal derivative amplifies the rounding of r2_ii (see test_oracle.py)
-    tol_g = 1e-6 if ('Exponential' in spec.kerns and len(spec.kerns) > 2) else 1e-9
+    # Folds of three / four kernels with an Exponential: measured 0.8e-9 .. 1.1e-9 (tools/tolerance_probe.py) -- the float64
+    # noise floor of the reference formula itself: k_ii = exp(-sqrt(r2_ii + 1e-12) / 2) with the gram-form r2_ii = a few
+    # 1e-16 |xs|^2 instead of 0 moves the kernel-variance slot by ~1e-9 between any two float64 evaluations (the DMMA
+    # epilogues of the one- and two-kernel models do not evaluate the diagonal of W K' at all and hold 1e-9).
+    tol_g = 5e-9 if ('Exponential' in spec.kerns and len(spec.kerns) > 2) else 1e-9
     check_ll_grad(spec, X, y, thetas, tol_g=tol_g)
 
 
@@ -374,8 +376,7 @@ def test_predict_grad_latent(name, N, M):
         assert np.max(np.abs(v - rv)) <= 1e-8 * max(np.max(np.abs(rv)), kv)
         # gradients are sums of N cancelling terms: compared relative to the largest component
         assert np.max(np.abs(dm - rdm)) <= 1e-8 * np.max(np.abs(rdm)), name
-        tol = 1e-6 if name == 'expo' else 1e-8   # Exponential: dk/dr2 ~ 1/r, see the module docstring of test_oracle
-        assert np.max(np.abs(dv - rdv)) <= tol * max(np.max(np.abs(rdv)), kv), name
+        assert np.max(np.abs(dv - rdv)) <= 1e-8 * max(np.max(np.abs(rdv)), kv), name
     # same values as the plain predict path
     m0, v0 = eng.predict(Xs)
     assert torch.allclose(m0, eng.predict_grad(Xs)[0], rtol=1e-12, atol=1e-14)
@@ -414,7 +415,7 @@ def test_predict_grad_epilogues():
                 assert np.max(np.abs(m - rm)) <= 1e-8 * np.max(np.abs(rm)), (stages, kw)
                 assert np.max(np.abs(v - rv)) <= 1e-8 * max(np.max(np.abs(rv)), np.max(rm ** 2)), (stages, kw)
                 assert np.max(np.abs(dm - rdm)) <= 1e-8 * np.max(np.abs(rdm)), (stages, kw)
-                assert np.max(np.abs(dv - rdv)) <= 1e-7 * max(np.max(np.abs(rdv)), np.max(np.abs(rdm))), (stages, kw)
+                assert np.max(np.abs(dv - rdv)) <= 1e-8 * max(np.max(np.abs(rdv)), np.max(np.abs(rdm))), (stages, kw)
 
 
 @pytest.mark.parametrize('name,N0,nadd', [('rbf', 100, 40), ('m52', 60, 70), ('sum', 120, 9)])
