@@ -794,6 +794,9 @@ extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int
                                gp->max_spins, gp->fault};
   if (!gp->hexec || !(key == gp->hkey)) {
     // capture: H2D of the points, flags, the 8-9 launches of the evaluation, D2H of the packed results
+    // (a replay the caller has not waited for yet finishes first: its graph is about to be destroyed)
+    e = cudaStreamSynchronize(gp->hstream);
+    if (e != cudaSuccess) return fail_cuda("host-call stream", e);
     host_graph_drop(gp);
     const bool prof = gp->profiling;
     gp->profiling = false;   // phase events cannot be recorded into a capture
