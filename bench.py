@@ -467,11 +467,12 @@ def main():
     eng.set_profiling(True)
     phases = {}
     reps = args.steps
-    for _ in range(reps):
-        eng.loglik_grad(theta_dev)          # the recorded call runs right behind another one, as inside the timed region
-        eng.loglik_grad(theta_dev)          # (the host sync that reads the events would otherwise let the GPU idle first)
-        for k, v in eng.phase_ms().items():
-            phases[k] = phases.get(k, 0.0) + v / reps
+    with ClockSampler(local) as clk_ph:
+        for _ in range(reps):
+            eng.loglik_grad(theta_dev)      # the recorded call runs right behind another one, as inside the timed region
+            eng.loglik_grad(theta_dev)      # (the host sync that reads the events would otherwise let the GPU idle first)
+            for k, v in eng.phase_ms().items():
+                phases[k] = phases.get(k, 0.0) + v / reps
     eng.set_profiling(False)
     fk_ms = phases['factor']
     fk_flops = B * flops_factor(N)
@@ -495,6 +496,7 @@ def main():
                        'algorithmic_bytes_per_launch': B * bytes_cov(N)},
         'step_frac': B * flops_ll(N, d) / (ms_per_step * 1e-3) / 1e12 / p64,
         'phase_ms': {k: round(v, 4) for k, v in phases.items() if v > 0},
+        'phase_clocks': clk_ph.summary(),
     }
 
     line = {
