@@ -43,6 +43,9 @@ struct avn_gp {
   cudaEvent_t ev[2 * AVN_PH_COUNT] = {};
   bool ev_used[AVN_PH_COUNT] = {};
   double acc_ms[AVN_PH_COUNT] = {};
+  // few samples: the output-warp column of warp_kernel runs on its own stream beside the input columns, scale and cov
+  cudaStream_t ystream = nullptr;
+  cudaEvent_t yev_fork = nullptr, yev_join = nullptr;
   // avn_gp_loglik_grad_host: the whole host-to-host evaluation captured once as a CUDA graph and replayed
   cudaStream_t hstream = nullptr;     // library-owned: stream capture is not allowed on the legacy default stream
   cudaEvent_t hev = nullptr;          // orders the replay behind the caller's stream
@@ -194,6 +197,9 @@ extern "C" void avn_gp_destroy(avn_gp* gp) {
   for (auto& s : gp->gstream)
     if (s) cudaStreamDestroy(s);
   host_graph_drop(gp);
+  if (gp->yev_fork) cudaEventDestroy(gp->yev_fork);
+  if (gp->yev_join) cudaEventDestroy(gp->yev_join);
+  if (gp->ystream) cudaStreamDestroy(gp->ystream);
   if (gp->hev) cudaEventDestroy(gp->hev);
   if (gp->hstream) cudaStreamDestroy(gp->hstream);
   delete gp;
@@ -392,7 +398,14 @@ static int ensure_ready(avn_gp* gp) {
 }
 
 // conversions + scaled inputs for B samples
-static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st) {
+// fork_y (out): set when the output column was launched on the handle's side stream -- the caller joins it with
+// join_warp_y before anything reads z / dz / wstat (the factor kernel).  Only asked for by loglik_group, only taken for few
+// samples of a model with a learnable output warp: that column (log, sinh-arcsinh, meanstd with block reductions: 65 us
+// for one sample of c2) is the longest of the kernel and nothing before the factorisation needs it, so it runs beside the
+// input columns (40 us), scale_kernel and the covariance build instead of in front of them.  Works inside a stream
+// capture as well (the side stream joins the capture through the fork event).
+static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W, int64_t npad, cudaStream_t st,
+                    bool* fork_y = nullptr) {
   Phase ph(gp, AVN_PH_WARP, st);
   // columns with a warp program are staged in shared memory when they fit (see warp_kernel)
   int max_np = -1;
@@ -401,11 +414,35 @@ static int run_warp(avn_gp* gp, const double* theta, int64_t B, const WsPtrs& W,
   if (gp->progs.yw.nstages > 0 && gp->progs.yw.nparams > max_np) max_np = gp->progs.yw.nparams;
   int64_t stage_doubles = max_np >= 0 ? gp->N * (1 + max_np) : 0;
   if (stage_doubles * 8 > kWarpStageMaxBytes) stage_doubles = 0;
-  warp_kernel<<<dim3((unsigned)gp->kd.d + 1, (unsigned)B), WARP_THREADS, (size_t)stage_doubles * 8, st>>>(
-      gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W, (int)stage_doubles);
+  const size_t smem = (size_t)stage_doubles * 8;
+  bool fork = fork_y && !gp->profiling && gp->progs.yw.nstages > 0 && B * (gp->kd.d + 1) <= gp->sm_count;
+  if (fork && !gp->ystream) {
+    cudaError_t e = cudaStreamCreateWithFlags(&gp->ystream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&gp->yev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&gp->yev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail_cuda("warp side stream", e);
+  }
+  if (fork) {
+    cudaError_t e = cudaEventRecord(gp->yev_fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(gp->ystream, gp->yev_fork, 0);
+    if (e != cudaSuccess) return fail_cuda("warp fork", e);
+    warp_kernel<<<dim3(1, (unsigned)B), WARP_THREADS, smem, gp->ystream>>>(gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad,
+                                                                           theta, W, (int)stage_doubles, gp->kd.d);
+    LAUNCH_CHECK("warp_kernel (output column)");
+    e = cudaEventRecord(gp->yev_join, gp->ystream);
+    if (e != cudaSuccess) return fail_cuda("warp join event", e);
+    *fork_y = true;
+  }
+  warp_kernel<<<dim3((unsigned)gp->kd.d + (fork ? 0 : 1), (unsigned)B), WARP_THREADS, smem, st>>>(
+      gp->kd, gp->progs, gp->X, gp->y, (int)gp->N, (int)npad, theta, W, (int)stage_doubles, 0);
   LAUNCH_CHECK("warp_kernel");
   scale_kernel<<<dim3((unsigned)((npad + 255) / 256), (unsigned)B), 256, 0, st>>>(gp->kd, (int)npad, theta, W);
   LAUNCH_CHECK("scale_kernel");
+  return 0;
+}
+static int join_warp_y(avn_gp* gp, cudaStream_t st) {
+  cudaError_t e = cudaStreamWaitEvent(st, gp->yev_join, 0);
+  if (e != cudaSuccess) return fail_cuda("warp join", e);
   return 0;
 }
 
@@ -632,15 +669,24 @@ static int launch_kinv_fast(bool optin_only, int kind, bool gx, dim3 grid, size_
 
 // the whole evaluation for samples [b0, b0+Bg) on one stream
 static int loglik_group(avn_gp* gp, const double* theta, int64_t Bg, double* ll, double* grad, int32_t* info,
-                        const WsPtrs& W, const avn_ws_layout& L, cudaStream_t st, bool single_sample = false) {
+                        const WsPtrs& W, const avn_ws_layout& L, cudaStream_t st, bool single_sample = false,
+                        bool single_group = false) {
   const KernDesc& kd = gp->kd;
   const int64_t npad = L.npad, nb = L.nb, ntiles = nb * (nb + 1) / 2;
   const bool want_grad = grad != nullptr;
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int32_t) * Bg, st);
   if (e != cudaSuccess) return fail_cuda("memset info", e);
-  int rc = run_warp(gp, theta, Bg, W, npad, st);
-  if (rc) return rc;
+  bool fork_y = false;
+  int rc = run_warp(gp, theta, Bg, W, npad, st, single_group ? &fork_y : nullptr);
+  if (rc) {
+    if (fork_y) join_warp_y(gp, st);   // a forked stream must rejoin (a capture could not end otherwise)
+    return rc;
+  }
   rc = run_cov(gp, theta, Bg, W, npad, W.kl, st);
+  if (fork_y) {
+    const int rj = join_warp_y(gp, st);
+    if (rc == 0) rc = rj;
+  }
   if (rc) return rc;
   rc = run_factor(gp, Bg, W, info, npad, true, st);   // beta = T z needs the inverse also without a gradient
   if (rc) return rc;
@@ -720,7 +766,7 @@ extern "C" int avn_gp_loglik_grad(avn_gp* gp, const double* theta_dev, int64_t B
     cudaError_t e = zero_flags(W, B, L.nb, st);
     if (e != cudaSuccess) return fail_cuda("memset flags", e);
   }
-  if (G <= 1) return loglik_group(gp, theta_dev, B, ll_dev, grad_dev, info_dev, W, L, st, B == 1);
+  if (G <= 1) return loglik_group(gp, theta_dev, B, ll_dev, grad_dev, info_dev, W, L, st, B == 1, true);
   for (int g = 0; g < G; g++)
     if (!gp->gstream[g]) {
       cudaError_t e = cudaStreamCreateWithFlags(&gp->gstream[g], cudaStreamNonBlocking);
@@ -809,7 +855,7 @@ extern "C" int avn_gp_loglik_grad_host(avn_gp* gp, const double* theta_host, int
     e = cudaMemcpyAsync(theta_dev, theta_host, (size_t)(B * P * 8), cudaMemcpyHostToDevice, hs);
     if (e == cudaSuccess) e = cudaMemsetAsync(info_dev, 0, (size_t)(B * 8), hs);   // whole [B] doubles slot of the int32 info
     if (e == cudaSuccess) e = zero_flags(W, B, L.nb, hs);
-    if (e == cudaSuccess) rc = loglik_group(gp, theta_dev, B, ll_dev, want_grad ? grad_dev : nullptr, info_dev, W, L, hs, B == 1);
+    if (e == cudaSuccess) rc = loglik_group(gp, theta_dev, B, ll_dev, want_grad ? grad_dev : nullptr, info_dev, W, L, hs, B == 1, true);
     if (e == cudaSuccess && rc == 0)
       e = cudaMemcpyAsync(out_host, packed, (size_t)(B * (P + 2) * 8), cudaMemcpyDeviceToHost, hs);
     cudaGraph_t graph = nullptr;

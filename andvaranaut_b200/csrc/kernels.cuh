@@ -42,14 +42,16 @@ constexpr int WSTAT = 16;
 constexpr int WARP_THREADS = 256;   // (512 threads: 85 -> 74 us at B = 1 but slower batched, and the block reductions change order)
 __global__ void __launch_bounds__(WARP_THREADS) warp_kernel(KernDesc kd, WarpProgs progs, const double* __restrict__ X,
                                                    const double* __restrict__ y, int N, int npad,
-                                                   const double* __restrict__ theta, WsPtrs ws, int stage_doubles) {
+                                                   const double* __restrict__ theta, WsPtrs ws, int stage_doubles,
+                                                   int col_begin) {
   // stage_doubles >= N (1 + nparams): the column and its parameter Jacobians live in dynamic shared memory while the
   // stages of the warp program run over them (every stage is a pass over the column, the data-dependent ones several
   // with block reductions between: on the strided global arrays each pass paid an L2 round trip per element -- 90 us of
   // a 1.1 ms evaluation at B = 1) and are written to their global layout once at the end.  Same arithmetic either way.
   extern __shared__ __align__(16) double wsm[];
   __shared__ double sh[192];
-  const int b = blockIdx.y, m = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  // col_begin: first column of this launch (0: all of them; d: only the output column, launched beside the input columns)
+  const int b = blockIdx.y, m = blockIdx.x + col_begin, tid = threadIdx.x, nt = blockDim.x;
   const double* th = theta + (int64_t)b * kd.P;
   if (m < kd.d) {
     double* xw = ws.xw + (int64_t)b * npad * kd.d + m;
