@@ -656,14 +656,14 @@ __global__ void __launch_bounds__(256) gx_reduce_kernel(int npad, int d, double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// finalisation: ll and gradient assembly.  grid (B, 1 + ceil(n_iw / 8) + ceil(n_cw / 8)), 256 threads: CTA y = 0 forms ll
-// and the kernel hyperparameter slots, the following CTAs take eight (dimension, parameter) pairs of the learnable input
-// warps each, the last ones eight output-warp parameters each -- one warp per pair as before (same summation order,
-// same bits), but the pairs of a sample no longer queue behind each other on ONE CTA (61 -> 2x us at B = 1, where this
-// kernel is latency-bound on strided L2 reads).
+// finalisation: ll and gradient assembly.  grid (B, 1 + n_iw + n_cw), 256 threads: CTA y = 0 forms ll and the kernel
+// hyperparameter slots, every following CTA takes ONE (dimension, parameter) pair of the learnable input warps or one
+// output-warp parameter: its eight warps sum eight contiguous row ranges (eight rows in flight per lane: the strided
+// reads are L2-latency bound), combined in a fixed order.  At B = 1 this kernel is pure latency: one CTA for everything
+// took 61 us, one warp per pair on three CTAs 34 us.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline int finalize_grid_y(int n_iw, int n_cw, int want_grad) {
-  return want_grad ? 1 + (n_iw + 7) / 8 + (n_cw + 7) / 8 : 1;
+  return want_grad ? 1 + n_iw + n_cw : 1;
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs progs, int N, int npad, int ntiles,
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
   // info = -1 with ll = NaN and a zero gradient -- distinct from a non-positive pivot (info > 0, ll = -inf).
   const bool aborted = ws.ctl[1] != 0;
   const bool bad = aborted || info[b] != 0;
-  const int role = blockIdx.y, n_iw_ctas = (kd.n_iw + 7) / 8;
+  const int role = blockIdx.y;   // 0: ll + kernel hyperparameters; 1 .. n_iw: input-warp pairs; then output-warp parameters
   const int warp = tid >> 5, lane = tid & 31;
   const int d = kd.d, nk = kd.nkern;
   double* gr = want_grad ? grad + (int64_t)b * kd.P : nullptr;
@@ -725,67 +725,64 @@ __global__ void __launch_bounds__(256) finalize_kernel(KernDesc kd, WarpProgs pr
     return;
   }
   if (!want_grad) return;
+  __shared__ double wred[8];
   if (bad) {
-    // this CTA's slice of the warp-parameter gradient
-    if (role <= n_iw_ctas) {
-      const int pq = (role - 1) * 8 + warp;
-      if (lane == 0 && pq < kd.n_iw) gr[kd.off_iw + pq] = 0.0;
-    } else {
-      const int q = (role - 1 - n_iw_ctas) * 8 + warp;
-      if (lane == 0 && q < kd.n_cw) gr[kd.off_cw + q] = 0.0;
+    // this CTA's entry of the warp-parameter gradient
+    if (tid == 0) {
+      if (role <= kd.n_iw) gr[kd.off_iw + role - 1] = 0.0;
+      else gr[kd.off_cw + role - 1 - kd.n_iw] = 0.0;
     }
     return;
   }
-  // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p.  One warp per (dimension, parameter) pair -- all pairs
-  // dealt to the 8 warps at once -- lanes stride over n (four rows in flight), one shuffle reduction, no barrier.
-  if (role <= n_iw_ctas) {
-    const int nb = npad / TILE;
+  // rows of this warp: eight contiguous ranges of whole 32-row groups
+  const int per = ((N + 255) / 256) * 32, n0 = warp * per, n1 = min(N, n0 + per);
+  double acc;
+  if (role <= kd.n_iw) {
+    // learnable input warps: sum_n G[n][m] * d xw[n][m] / d p
+    const int nb = npad / TILE, pq = role - 1;
     // G[n][m] = sum over source tiles, already reduced into slab 0 by gx_reduce_kernel
     const double* G = ws.gxpart + (int64_t)b * nb * npad * d;
-    for (int pq = (role - 1) * 8 + warp; pq < min(kd.n_iw, role * 8); pq += 8) {
-      // pair index -> (dimension m, parameter q of its warp)
-      int m = 0, q = pq;
-      for (;; m++) {
-        const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;
-        if (q < np) break;
-        q -= np;
-      }
-      const double* Gm = G + m;
-      const double* Dm = ws.dxw + (((int64_t)b * npad) * d + m) * MAXWP + q;
-      // eight rows in flight per lane (the loads are strided and L2-latency bound), fixed summation order
-      double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      int n = lane;
-      for (; n + 224 < N; n += 256) {
-        double gv[8], dv[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          gv[u] = Gm[(int64_t)(n + 32 * u) * d];
-          dv[u] = Dm[(int64_t)(n + 32 * u) * d * MAXWP];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) a[u] = fma(gv[u], dv[u], a[u]);
-      }
-      for (; n < N; n += 32) a[0] = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a[0]);
-      const double acc = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
-      if (lane == 0) gr[kd.off_iw + pq] = acc;
+    int m = 0, q = pq;   // pair index -> (dimension m, parameter q of its warp)
+    for (;; m++) {
+      const int np = progs.xw[m].nstages > 0 ? progs.xw[m].nparams : 0;
+      if (q < np) break;
+      q -= np;
     }
-  }
-  // learnable output warp: -alpha^T dz/dp + sum d log g'/dp
-  if (role > n_iw_ctas) {
+    const double* Gm = G + m;
+    const double* Dm = ws.dxw + (((int64_t)b * npad) * d + m) * MAXWP + q;
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int n = n0 + lane;
+    for (; n + 224 < n1; n += 256) {
+      double gv[8], dv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        gv[u] = Gm[(int64_t)(n + 32 * u) * d];
+        dv[u] = Dm[(int64_t)(n + 32 * u) * d * MAXWP];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) a[u] = fma(gv[u], dv[u], a[u]);
+    }
+    for (; n < n1; n += 32) a[0] = fma(Gm[(int64_t)n * d], Dm[(int64_t)n * d * MAXWP], a[0]);
+    acc = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
+  } else {
+    // learnable output warp: -alpha^T dz/dp (+ sum d log g'/dp below)
     const double* al = ws.alpha + (int64_t)b * npad;
-    const int r0 = role - 1 - n_iw_ctas;
-    for (int q = r0 * 8 + warp; q < min(kd.n_cw, (r0 + 1) * 8); q += 8) {
-      const double* Dz = ws.dz + (int64_t)b * npad * MAXWP + q;
-      double a[4] = {0.0, 0.0, 0.0, 0.0};
-      int n = lane;
-      for (; n + 96 < N; n += 128) {
+    const double* Dz = ws.dz + (int64_t)b * npad * MAXWP + (role - 1 - kd.n_iw);
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int n = n0 + lane;
+    for (; n + 224 < n1; n += 256) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) a[u] = fma(al[n + 32 * u], Dz[(int64_t)(n + 32 * u) * MAXWP], a[u]);
-      }
-      for (; n < N; n += 32) a[0] = fma(al[n], Dz[(int64_t)n * MAXWP], a[0]);
-      double acc = warp_sum((a[0] + a[1]) + (a[2] + a[3]));
-      if (lane == 0) gr[kd.off_cw + q] = -acc + wst[1 + q];
+      for (int u = 0; u < 8; u++) a[u] = fma(al[n + 32 * u], Dz[(int64_t)(n + 32 * u) * MAXWP], a[u]);
     }
+    for (; n < n1; n += 32) a[0] = fma(al[n], Dz[(int64_t)n * MAXWP], a[0]);
+    acc = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
+  }
+  if (lane == 0) wred[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    const double tot = ((wred[0] + wred[1]) + (wred[2] + wred[3])) + ((wred[4] + wred[5]) + (wred[6] + wred[7]));
+    if (role <= kd.n_iw) gr[kd.off_iw + role - 1] = tot;
+    else gr[kd.off_cw + role - 1 - kd.n_iw] = -tot + wst[1 + role - 1 - kd.n_iw];
   }
 }
 
