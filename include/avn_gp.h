@@ -16,8 +16,11 @@
  *     by the caller; the library allocates nothing on the device and never frees caller memory.
  *     (One exception: a library built with -DAVN_FACTOR_PROF, an instrumentation build that is never shipped,
  *     keeps one small static counter buffer of its own.)
- *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*) and is asynchronous;
- *     only avn_gp_create/avn_gp_destroy/avn_gp_set_data touch no stream.
+ *   - all work is ordered on the caller's stream (a cudaStream_t passed as void*) and is asynchronous;
+ *     only avn_gp_create/avn_gp_destroy/avn_gp_set_data touch no stream.  The library owns a few non-blocking side
+ *     streams per handle (sample groups of avn_gp_set_streams, the output-warp column of calls with few samples, the
+ *     replayed graph of avn_gp_loglik_grad_host): each is forked from and joined back into the caller's stream by
+ *     events inside the call, so the caller sees plain stream order.
  *   - a handle is bound to ONE device: the device that is current when avn_gp_create runs (or, when none is
  *     visible then, when the first call that enqueues work runs).  Every such call makes that device current for
  *     its duration and restores the caller's afterwards, so handles may be used from any host thread and handles
