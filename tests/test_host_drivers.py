@@ -371,3 +371,18 @@ def test_batched_restarts_propagate_an_evaluation_failure_without_hanging():
     t.join(timeout=60)
     assert not t.is_alive(), 'find_map_multi hung after a failed evaluation'
     assert isinstance(res['out'], Boom)
+
+
+def test_theta_only_equals_theta_from_z():
+    """the drivers launch the device evaluation on ParamSpace.theta_only(z) and form the Jacobian terms afterwards: it
+    must be the first output of theta_from_z bit for bit, for every prior family / transform and for batches."""
+    from andvaranaut_b200.priors import ParamSpace
+    rng = np.random.default_rng(5)
+    for truncate in (False, True):
+        for kw in (dict(nx=3, nkern=1, noise=True),
+                   dict(nx=8, nkern=1, noise=True, n_iw=16, cw_pos=[False, True, False, True]),
+                   dict(nx=2, nkern=3, noise=False, has_alpha=True)):
+            sp = ParamSpace(truncate=truncate, **kw)
+            z = rng.normal(size=(7, sp.P)) * 2.0
+            assert np.array_equal(sp.theta_only(z), sp.theta_from_z(z)[0])
+            assert np.array_equal(sp.theta_only(z[0]), sp.theta_from_z(z[0])[0])
