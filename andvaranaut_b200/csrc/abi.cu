@@ -118,7 +118,7 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 static inline int64_t npad_of(int64_t N) { return align_up(N < 1 ? 1 : N, TILE); }
 
 extern "C" const char* avn_last_error(void) { return g_err.c_str(); }
-extern "C" int avn_version(void) { return 100; }
+extern "C" int avn_version(void) { return 110; }   // 110: avn_gp_loglik_grad_host / avn_gp_host_wait / avn_gp_host_staging_bytes
 
 extern "C" int avn_gp_create(const avn_model_desc* desc, avn_gp** out) {
   if (!desc || !out) return fail("avn_gp_create: null argument");
