@@ -655,6 +655,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
   __shared__ int s_ticket;
   __shared__ int s_known;
   __shared__ int s_bad;
+  __shared__ int s_tkk;   // throughput launches: T_kk was there when the task started (its tile is prefetched, see P / R)
   __shared__ __align__(16) double s_dval[TILE];
   __shared__ __align__(16) double s_inv[TILE];
   using FacKK = typename FacCfg<FUSED>::KK;
@@ -912,12 +913,36 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       const int i = idx, i0 = i * TILE;
       double* Aik = L + (int64_t)i0 * npad + k0;
       if (i == k + 1) FEVENT(1, k, 0);
+      // Throughput launches: a panel / inverse task of step k usually starts long after T_kk was published.  Thread 0 looks
+      // at the flag when the task starts; if T_kk is there, its tile is fetched by cp.async into the pipeline stage that
+      // falls free while the last slab is multiplied (one 32-deep stage holds a staged 64 x 64 tile), and S goes to the
+      // other stage -- the flag's round trip and the staging round (~1.7 us in front of every epilogue) are gone.
+      constexpr bool PREFETCH_TKK = !FUSED && FacKK::STAGES == 2 && FacKK::STAGE_DOUBLES >= TILE * FAC_LDS &&
+                                    FacKR::STAGE_DOUBLES >= TILE * FAC_LDS;
+      double* sS = sA;    // where S and T_kk are staged for the epilogue
+      double* sTk = sB;
+      bool have_tkk = false;
       FacKK g;
       load_neg_tile(g.acc, Aik, npad, wm, wn, gq, t);
       if (k > 0) {
+        if (PREFETCH_TKK && tid == 0) s_tkk = ld_acquire(tflag + k) >= k + 1;
         SlabWaiter w{lflag + i, lflag + k, fa.ctl, &s_known, 0, 0, fa.max_spins, nullptr, 0, FAC_SPB};
-        g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
-              [&](int kt) { w(kt); });
+        if constexpr (PREFETCH_TKK) {
+          const double* Tkk_g = T + (int64_t)k0 * npad + k0;
+          g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
+                [&](int kt) { w(kt); }, 0, [&](double* buf) {
+                  if (s_tkk) stage_tile_async(buf, Tkk_g, npad);
+                });
+          have_tkk = s_tkk != 0;
+          if (have_tkk) {
+            const int KT = k0 / FacKK::BK;
+            sTk = smem + (KT % 2) * FacKK::STAGE_DOUBLES;
+            sS = smem + ((KT + 1) % 2) * FacKK::STAGE_DOUBLES;
+          }
+        } else {
+          g.run(smem, L + (int64_t)i0 * npad, npad, min(TILE, fa.n - i0), L + (int64_t)k0 * npad, npad, 64, k0,
+                [&](int kt) { w(kt); });
+        }
         FPROF(2);
       }
 #pragma unroll
@@ -925,7 +950,7 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + j * 8 + 2 * t;
-          *reinterpret_cast<double2*>(&sA[r * FAC_LDS + c]) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
+          *reinterpret_cast<double2*>(&sS[r * FAC_LDS + c]) = make_double2(-g.acc[ii][j][0], -g.acc[ii][j][1]);
         }
       if (FUSED && i == k + 1) {
         // fused-panel launches: S goes to the unused tile (i,k) of the T slab for D(b,i) (see there)
@@ -941,15 +966,19 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       }
       FPROF(4);
       if (i == k + 1) FEVENT(1, k, 1);
-      wait_flag(tflag + k, k + 1, fa.ctl, fa.max_spins);   // T[k,k] is there (also orders the sA writes)
-      FPROF(3);
-      if (i == k + 1) FEVENT(1, k, 2);
-      stage_tile(sB, T + (int64_t)k0 * npad + k0, npad);
-      __syncthreads();
+      if (have_tkk) {
+        __syncthreads();   // S is staged (T_kk arrived inside run())
+      } else {
+        wait_flag(tflag + k, k + 1, fa.ctl, fa.max_spins);   // T[k,k] is there (also orders the S writes)
+        FPROF(3);
+        if (i == k + 1) FEVENT(1, k, 2);
+        stage_tile(sTk, T + (int64_t)k0 * npad + k0, npad);
+        __syncthreads();
+      }
       // X = S T_kk^T (panel_product), straight from the accumulators to the tile's place in L
       {
         double xa[8][2][2];
-        panel_product(xa, sA, sB, warp, gq, t);
+        panel_product(xa, sS, sTk, warp, gq, t);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
           const int jf = c ? 7 - warp : warp;
@@ -967,25 +996,49 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
       // ---------------- R(b,k,j) ----------------
       if (!fa.want_inverse) continue;
       const int j = idx, j0 = j * TILE;
+      // (T_kk prefetched into the free pipeline stage as in the panel tasks; here T_kk is the A operand, S the B operand)
+      constexpr bool PREFETCH_TKK = !FUSED && FacKR::STAGES == 2 && FacKR::STAGE_DOUBLES >= TILE * FAC_LDS;
+      double* sS = sB;
+      double* sTk = sA;
+      bool have_tkk = false;
       FacKR g;
       g.zero();
+      if (PREFETCH_TKK && tid == 0) s_tkk = ld_acquire(tflag + k) >= k + 1;
       SlabWaiter w{lflag + k, tflag + j, fa.ctl, &s_known, j, 0, fa.max_spins, nullptr, 0, FAC_SPB};
       // first slab: B = T[j,j] is lower triangular, its columns n >= 32 vanish for the first 32 k
-      g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
-            [&](int kt) { w(kt); }, wn == 1 ? 32 / FAC_BK : 0);
+      if constexpr (PREFETCH_TKK) {
+        const double* Tkk_g = T + (int64_t)k0 * npad + k0;
+        g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
+              [&](int kt) { w(kt); }, wn == 1 ? 32 / FAC_BK : 0, [&](double* buf) {
+                if (s_tkk) stage_tile_async(buf, Tkk_g, npad);
+              });
+        have_tkk = s_tkk != 0;
+        if (have_tkk) {
+          const int KT = (k0 - j0) / FacKR::BK;
+          sTk = smem + (KT % 2) * FacKR::STAGE_DOUBLES;
+          sS = smem + ((KT + 1) % 2) * FacKR::STAGE_DOUBLES;
+        }
+      } else {
+        g.run(smem, L + (int64_t)k0 * npad + j0, npad, rows_k, T + (int64_t)j0 * npad + j0, npad, 64, k0 - j0,
+              [&](int kt) { w(kt); }, wn == 1 ? 32 / FAC_BK : 0);
+      }
       FPROF(2);
 #pragma unroll
       for (int ii = 0; ii < 4; ii++)
 #pragma unroll
         for (int jj = 0; jj < 4; jj++) {
           const int r = wm * 32 + ii * 8 + gq, c = wn * 32 + jj * 8 + 2 * t;
-          *reinterpret_cast<double2*>(&sB[r * FAC_LDS + c]) = make_double2(g.acc[ii][jj][0], g.acc[ii][jj][1]);
+          *reinterpret_cast<double2*>(&sS[r * FAC_LDS + c]) = make_double2(g.acc[ii][jj][0], g.acc[ii][jj][1]);
         }
       FPROF(4);
-      wait_flag(tflag + k, k + 1, fa.ctl, fa.max_spins);
-      FPROF(3);
-      stage_tile(sA, T + (int64_t)k0 * npad + k0, npad);
-      __syncthreads();
+      if (have_tkk) {
+        __syncthreads();
+      } else {
+        wait_flag(tflag + k, k + 1, fa.ctl, fa.max_spins);
+        FPROF(3);
+        stage_tile(sTk, T + (int64_t)k0 * npad + k0, npad);
+        __syncthreads();
+      }
       // T[k,j] = -T_kk S on 8 x 8 fragments.  T_kk is lower triangular: the fragment row fr needs k < 8 fr + 8 only.  Warp w
       // takes the fragment rows w and 7 - w (balanced as in the panel tasks) and all eight column fragments.
       {
@@ -998,9 +1051,9 @@ __global__ void __launch_bounds__(FAC_THREADS, FUSED ? 2 : 3) factor_kernel(Fact
           const int kmax = 8 * fr + 8;
 #pragma unroll 2
           for (int kk = 0; kk < kmax; kk += 4) {
-            const double av = sA[(8 * fr + gq) * FAC_LDS + kk + t];
+            const double av = sTk[(8 * fr + gq) * FAC_LDS + kk + t];
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) dmma884(xr[c][jj][0], xr[c][jj][1], av, sB[(kk + t) * FAC_LDS + 8 * jj + gq]);
+            for (int jj = 0; jj < 8; jj++) dmma884(xr[c][jj][0], xr[c][jj][1], av, sS[(kk + t) * FAC_LDS + 8 * jj + gq]);
           }
         }
         double* Tkj = T + (int64_t)k0 * npad + j0;

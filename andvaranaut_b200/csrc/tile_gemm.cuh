@@ -137,6 +137,17 @@ struct TileGemm {
   template <typename PreIssue>
   __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda, int a_rows, const double* Bpt,
                                       int64_t ldb, int b_rows, int klen, PreIssue pre_issue, int skip_kt = 0) {
+    run(smem, Apt, lda, a_rows, Bpt, ldb, b_rows, klen, pre_issue, skip_kt, [](double*) {});
+  }
+
+  // As above; tail_issue(buf) is called once by every thread (uniformly) in the first iteration that has no k-slab left
+  // to load: `buf` is the stage buffer that just became free (STAGE_DOUBLES doubles).  The caller may start cp.async
+  // copies of whatever its epilogue needs into it -- they travel while the last STAGES - 1 slabs are multiplied and are
+  // complete when run() returns (it ends with wait_group 0 and a barrier).  Not called when klen < BK.
+  template <typename PreIssue, typename TailIssue>
+  __device__ __forceinline__ void run(double* smem, const double* Apt, int64_t lda, int a_rows, const double* Bpt,
+                                      int64_t ldb, int b_rows, int klen, PreIssue pre_issue, int skip_kt,
+                                      TailIssue tail_issue) {
     const int tid = threadIdx.x;
     const int warp = (tid >> 5) ^ swz, lane = tid & 31;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
@@ -168,6 +179,8 @@ struct TileGemm {
         if (nk < KT) {
           pre_issue(nk);
           issue(nk);
+        } else if (nk == KT) {
+          tail_issue(smem + (nk % STAGES) * STAGE_DOUBLES);
         }
         cp_async_commit();
         const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
