@@ -540,3 +540,25 @@ def test_captured_host_call_equals_device_path():
         ll, gr, info = eng.loglik_grad(ths)
         hl, hg, hi = eng.loglik_grad_host(ths)
         assert np.array_equal(hl, ll.cpu().numpy()) and np.array_equal(hg, gr.cpu().numpy())
+
+
+def test_few_sample_launches_equal_batched_launch_with_warps():
+    """A model with learnable input and output warps evaluated one sample at a time takes the few-sample launches (the
+    output-warp column on a side stream, the chain instantiation of the factor kernel, the single-sample gradient kernel,
+    finalize per pair); inside a batch of 40 it takes none of them.  Same arithmetic: every row of the batch equals its
+    one-at-a-time evaluation bit for bit, through the device-tensor call and through the captured host call."""
+    spec = go.ModelSpec(nx=3, kerns=['Matern52'], xwarps=[(['uniform', 'kumaraswamy'], (0.0, 1.0))] * 3,
+                        ywarp=['logarithm', 'sal', 'meanstd'])
+    X, y, th, _ = cases.synth(spec, 330, seed=41)
+    rng = np.random.default_rng(2)
+    thetas = th[None, :] * np.exp(0.03 * rng.normal(size=(40, len(th))))
+    eng = engine(spec)
+    eng.set_data(X, y)
+    ll, grad, info = (t.cpu().numpy() for t in eng.loglik_grad(thetas))
+    assert not info.any()
+    for b in (0, 7, 39):
+        l1, g1, i1 = (t.cpu().numpy() for t in eng.loglik_grad(thetas[b:b + 1]))
+        assert i1[0] == 0 and l1[0] == ll[b] and np.array_equal(g1[0], grad[b])
+        for _ in range(2):        # second call of the batch size: the captured graph
+            hl, hg, hi = eng.loglik_grad_host(thetas[b:b + 1])
+        assert hi[0] == 0 and hl[0] == ll[b] and np.array_equal(hg[0], grad[b])
